@@ -1,0 +1,193 @@
+/*
+ * mcg_b200.h -- C ABI of libmcg_b200.so, the B200 (sm_100a) featurise + score path
+ * of MetaCoAG.
+ *
+ * The reference (MetaCoAG v1.1.5) is pure Python and defines NO FFI of its own
+ * (SURVEY.md section 8b): its boundary is the module API of
+ * metacoag_utils/{feature_utils,matching_utils,label_prop_utils}.py.  Each entry
+ * point below names the reference function(s) (file:line under the reference
+ * root) whose arithmetic it replaces; metacoag_b200/*.py keeps those Python
+ * signatures and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every host buffer is caller-owned,
+ *     C-contiguous and alive for the duration of the call;
+ *   - device memory is owned by the context (mcg_ctx) and freed by mcg_destroy;
+ *   - every call returns 0 (MCG_OK) or a negative code; mcg_last_error() gives
+ *     the message.  Nothing throws or exits across this boundary;
+ *   - a context is bound to one CUDA device and is internally mutex-guarded
+ *     (label_prop_utils.assign_long is entered from several Python threads,
+ *     metacoag:959-999, and ctypes drops the GIL);
+ *   - there is no CPU fallback: without a CUDA device mcg_create() fails.
+ */
+#ifndef MCG_B200_H
+#define MCG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCG_NPROF 136 /* canonical tetramers, feature_utils.py:38-57 */
+
+enum {
+    MCG_OK = 0,
+    MCG_ERR_CUDA = -1,   /* CUDA runtime failure (message has the CUDA error string) */
+    MCG_ERR_ARG = -2,    /* bad argument */
+    MCG_ERR_STATE = -3,  /* called before the data it needs was loaded */
+    MCG_ERR_DOMAIN = -4, /* the reference would raise here: ZeroDivisionError in
+                            get_comp_probability (matching_utils.py:36-39, both Gaussians
+                            underflow at distance >~ 1.39) */
+    MCG_ERR_NOMEM = -5
+};
+
+enum { MCG_ENC_ASCII = 0, MCG_ENC_2BIT = 1 };
+enum { MCG_RULE_A = 0, MCG_RULE_B = 1 };
+
+typedef struct mcg_ctx mcg_ctx;
+
+/* ---- context ---------------------------------------------------------------- */
+int mcg_device_count(void);
+mcg_ctx *mcg_create(int device);       /* NULL on failure; mcg_last_error(NULL) says why */
+void mcg_destroy(mcg_ctx *ctx);
+const char *mcg_last_error(const mcg_ctx *ctx);
+/* Run on a caller-provided CUDA stream (e.g. torch's current stream, so that the
+ * NCCL collectives the host issues are stream-ordered after the kernels); NULL
+ * restores the context's own stream. */
+int mcg_set_stream(mcg_ctx *ctx, void *cuda_stream);
+int mcg_synchronize(mcg_ctx *ctx);
+/* Pinned host memory for the buffers handed to the calls below (optional). */
+void *mcg_host_alloc(size_t bytes);
+void mcg_host_free(void *p);
+
+/* ---- featurisation ---------------------------------------------------------- */
+/* feature_utils.py:38-57 compute_kmer_inds(4): code -> slot of the canonical
+ * tetramer, code = b0<<6|b1<<4|b2<<2|b3 with A0 C1 G2 T3 (feature_utils.py:31-35).
+ * Pure host arithmetic (a 256-entry table); the kernels use the same table. */
+int mcg_kmer_table(uint8_t table[256]);
+
+/* feature_utils.py:60-70 count_kmers / :73-119 get_tetramer_profiles.
+ * bases: concatenated contigs; offsets[n+1] in bases.  MCG_ENC_ASCII: one byte
+ * per base, A0 C1 G2 T3 and ANY other byte 0 (lower case and N included,
+ * feature_utils.py:21).  MCG_ENC_2BIT: base i of contig c is bits [2j,2j+2) of
+ * 32-bit word pk_word(c) + i/16, j = i%16, each contig starting on a 16-byte
+ * boundary: pk_word(c) = sum_{k<c} 4*ceil(len_k/64)  (offsets still in bases).
+ * counts [n,136] uint32 and/or freqs [n,136] float64 (either may be NULL);
+ * freqs = counts / max(1, len-3), IEEE division, bit-exact with the reference.
+ * Stateless: nothing stays resident. */
+int mcg_tetramer_scan(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n,
+                      int encoding, uint32_t *counts, double *freqs);
+
+/* Resident form: upload + pack the contigs once, scan on the device, keep the
+ * normalised profiles in the context as the contig table the scorers read. */
+int mcg_load_contigs(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n,
+                     int encoding);
+int mcg_scan(mcg_ctx *ctx);
+int mcg_get_profiles(mcg_ctx *ctx, int64_t first, int64_t n, uint32_t *counts, double *freqs);
+/* Contig table from host profiles (the dict the Python API carries around). */
+int mcg_set_profiles(mcg_ctx *ctx, const double *prof /* [n,136] */, int64_t n);
+
+/* feature_utils.py:150-153 (clamp < 1e-4 -> 1e-4) plus the per-(contig, sample)
+ * terms get_cov_probability recomputes for every pair (matching_utils.py:48-54):
+ * log(c) and lgamma(c + 1) -- the latter as CPython's math.lgamma computes it
+ * (Lanczos, g = 6.0246800407767296), not libm's.  cov [n,S]. */
+int mcg_load_coverage(mcg_ctx *ctx, const double *cov, int64_t n, int n_samples);
+int mcg_get_coverage_terms(mcg_ctx *ctx, double *cov, double *logc, double *lgam);
+
+/* feature_utils.py:217-235 get_bin_profiles: per bin, the mean of the member rows
+ * (rows added in member order, one division).  members: contig ids, CSR by
+ * seg_offsets[nseg+1].  Outputs [nseg,136] and [nseg,S] (either may be NULL). */
+int mcg_bin_profiles(mcg_ctx *ctx, const int64_t *members, const int64_t *seg_offsets,
+                     int64_t nseg, double *cen_prof, double *cen_cov);
+
+/* ---- scoring ---------------------------------------------------------------- */
+/* Elementwise forms of matching_utils.py:21-66 (normpdf, get_tetramer_distance,
+ * get_comp_probability, get_cov_probability) over n independent inputs. */
+int mcg_normpdf(mcg_ctx *ctx, const double *x, double mean, double sd, double *out, int64_t n);
+int mcg_tetramer_distance(mcg_ctx *ctx, const double *u, const double *v, int64_t n, int width,
+                          double *out);
+int mcg_comp_probability(mcg_ctx *ctx, const double *dist, double *out, int64_t n);
+int mcg_cov_probability(mcg_ctx *ctx, const double *cov1, const double *cov2, int64_t n,
+                        int n_samples, double *out);
+
+/* All-pairs primitives between resident contigs: queries[nq] x targets[nt] ->
+ * dist / prob_comp / prob_cov / lp, each [nq,nt] or NULL; lp = -(log10 pc + log10 pv)
+ * when pc*pv > 0 else MAX_WEIGHT (DBL_MAX).  Diagnostic / parity form of the inner
+ * loop of matching_utils.py:123-147. */
+int mcg_pair_scores(mcg_ctx *ctx, const int64_t *queries, int64_t nq, const int64_t *targets,
+                    int64_t nt, double *dist, double *pc, double *pv, double *lp);
+
+/* Rule C -- label_prop_utils.py:308-345 assign_long for a batch of contigs
+ * (metacoag:947-999 calls it once per long unbinned contig) and the bin x bin merge
+ * scoring of metacoag:1104-1140 when the queries are themselves centroids.
+ * queries: contig ids or NULL for 0..nq-1.  cen_prof [B,136], cen_cov [B,S]
+ * (NULL, NULL = the centroids left resident by mcg_bin_profiles).
+ * weights [nq,B] or NULL; argmin[nq] = first index of the minimum, -1 where the
+ * reference returns None (minimum is MAX_WEIGHT); wmin[nq]. */
+int mcg_score_centroids(mcg_ctx *ctx, const int64_t *queries, int64_t nq, const double *cen_prof,
+                        const double *cen_cov, int64_t n_bins, double *weights, int32_t *argmin,
+                        double *wmin);
+
+/* Rules A and B -- the (query x bin x member) loops of matching_utils.py:117-155,
+ * 368-398 (A: sum / n_members) and label_prop_utils.py:54-86 (B: sum / n_valid).
+ * members/seg_offsets: CSR of the member contigs to score per bin.  weights [nq,nseg]. */
+int mcg_score_members(mcg_ctx *ctx, const int64_t *queries, int64_t nq, const int64_t *members,
+                      const int64_t *seg_offsets, int64_t nseg, int rule, double *weights);
+
+/* ---- label-propagation frontier ---------------------------------------------- */
+/* label_prop_utils.py:24-100 run_bfs_long for a batch of start nodes over the
+ * CSR assembly graph (neighbours in ascending id order, what igraph gives after
+ * simplify()): bounded FIFO BFS that stops at labelled nodes and reproduces the
+ * reference's depth-overwrite behaviour (:93-98).  labels[v] = bin or -1.
+ * For start node i, hits are written at hit_offsets[i] .. : (labelled node, bin,
+ * depth); the score of (start, bin) is rule B and comes from mcg_score_members.
+ * max_hits_per_node bounds the per-node output; n_hits[i] is the true count
+ * (a count above the bound means the caller must retry with a larger bound). */
+int mcg_bfs_candidates(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
+                       int64_t n_vertices, const int32_t *labels, const int64_t *starts,
+                       int64_t n_starts, int depth_limit, int max_hits_per_node,
+                       int32_t *hit_node, int32_t *hit_bin, int32_t *hit_depth,
+                       int32_t *n_hits);
+
+/* ---- fused plug-in call and the resident step ---------------------------------- */
+/* Featurise + score in one call from HOST buffers: upload, pack, scan, normalise,
+ * coverage terms, rule-C scoring against the given centroids, download
+ * (argmin, wmin).  Leaves profiles and coverage terms resident. */
+int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n,
+                        int encoding, const double *cov, int n_samples, const double *cen_prof,
+                        const double *cen_cov, int64_t n_bins, int32_t *argmin, double *wmin);
+
+/* Same work on data already resident (mcg_load_contigs + coverage uploaded with
+ * mcg_load_coverage, centroids with mcg_set_centroids): scan -> normalise -> coverage
+ * terms -> rule C; results stay on the device (d_argmin int32[n], d_wmin f64[n] are
+ * DEVICE pointers, or NULL to use context-owned buffers). */
+int mcg_set_centroids(mcg_ctx *ctx, const double *cen_prof, const double *cen_cov,
+                      int64_t n_bins);
+int mcg_step_resident(mcg_ctx *ctx, void *d_argmin, void *d_wmin);
+int mcg_get_assignments(mcg_ctx *ctx, int32_t *argmin, double *wmin);
+
+/* Per-kernel device times of the last mcg_step_resident / mcg_featurise_score,
+ * measured with CUDA events on the launching stream when profiling is on.
+ * Slots: 0 pack, 1 scan, 2 normalise, 3 coverage terms, 4 score, 5 h2d, 6 d2h. */
+#define MCG_N_TIMERS 8
+int mcg_profile(mcg_ctx *ctx, int on);
+int mcg_timings(mcg_ctx *ctx, float *ms /* [MCG_N_TIMERS] */, int64_t *launches);
+
+/* ---- synthetic workloads (bench / tests) ------------------ */
+/* Fill a device-generated ASCII contig set: per-genome first-order Markov bases,
+ * n_frac of positions overwritten with 'N', lower_frac of contigs lower-cased.
+ * bases (host, may be pinned) receives sum(len) bytes. */
+int mcg_synth_bases(mcg_ctx *ctx, const int64_t *offsets, int64_t n, const int32_t *genome_of,
+                    const float *trans /* [n_genomes,4,4] row-stochastic */, int n_genomes,
+                    uint64_t seed, double n_frac, double lower_frac, uint8_t *bases);
+
+/* FP64 FMA throughput of this device (dependent-free DFMA loop), the roofline
+ * denominator of the scoring kernel.  TFLOP/s. */
+int mcg_fp64_peak(mcg_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCG_B200_H */

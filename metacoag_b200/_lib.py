@@ -1,0 +1,426 @@
+"""ctypes binding of libmcg_b200.so (include/mcg_b200.h).
+
+This is the only compute path of the package.  If the shared library is missing, or there
+is no CUDA device, everything here raises: there is no CPU fallback and nothing in this
+package imports ``oracle/``.
+"""
+import ctypes
+import os
+import sys
+import threading
+
+import numpy as np
+
+NPROF = 136
+MAX_WEIGHT = sys.float_info.max
+ENC_ASCII, ENC_2BIT = 0, 1
+RULE_A, RULE_B = 0, 1
+N_TIMERS = 8
+TIMER_NAMES = ("pack", "scan", "normalise", "cov_terms", "score", "h2d", "d2h", "other")
+
+OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_DOMAIN, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcg_b200.so")
+
+_c = ctypes
+_vp, _i64, _int, _dbl = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_double
+
+# name -> (restype, argtypes); the list tests/test_abi.py checks against the header
+SIGNATURES = {
+    "mcg_device_count": (_int, []),
+    "mcg_create": (_vp, [_int]),
+    "mcg_destroy": (None, [_vp]),
+    "mcg_last_error": (_c.c_char_p, [_vp]),
+    "mcg_set_stream": (_int, [_vp, _vp]),
+    "mcg_synchronize": (_int, [_vp]),
+    "mcg_host_alloc": (_vp, [_c.c_size_t]),
+    "mcg_host_free": (None, [_vp]),
+    "mcg_kmer_table": (_int, [_vp]),
+    "mcg_tetramer_scan": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "mcg_load_contigs": (_int, [_vp, _vp, _vp, _i64, _int]),
+    "mcg_scan": (_int, [_vp]),
+    "mcg_get_profiles": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "mcg_set_profiles": (_int, [_vp, _vp, _i64]),
+    "mcg_load_coverage": (_int, [_vp, _vp, _i64, _int]),
+    "mcg_get_coverage_terms": (_int, [_vp, _vp, _vp, _vp]),
+    "mcg_bin_profiles": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "mcg_normpdf": (_int, [_vp, _vp, _dbl, _dbl, _vp, _i64]),
+    "mcg_tetramer_distance": (_int, [_vp, _vp, _vp, _i64, _int, _vp]),
+    "mcg_comp_probability": (_int, [_vp, _vp, _vp, _i64]),
+    "mcg_cov_probability": (_int, [_vp, _vp, _vp, _i64, _int, _vp]),
+    "mcg_pair_scores": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "mcg_score_centroids": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mcg_score_members": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _vp]),
+    "mcg_bfs_candidates": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _vp, _vp,
+                                  _vp, _vp]),
+    "mcg_featurise_score": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _i64, _vp,
+                                   _vp]),
+    "mcg_set_centroids": (_int, [_vp, _vp, _vp, _i64]),
+    "mcg_step_resident": (_int, [_vp, _vp, _vp]),
+    "mcg_get_assignments": (_int, [_vp, _vp, _vp]),
+    "mcg_profile": (_int, [_vp, _int]),
+    "mcg_timings": (_int, [_vp, _vp, _vp]),
+    "mcg_synth_bases": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _c.c_uint64, _dbl, _dbl, _vp]),
+    "mcg_fp64_peak": (_int, [_vp, _vp]),
+}
+
+
+class McgError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libmcg_b200: %s (code %d)" % (message, code))
+        self.code = code
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the shared library and declare every prototype.  Raises if it is missing."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    "%s not found: build it with `python -m metacoag_b200.build` "
+                    "(there is no CPU fallback)" % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (restype, argtypes) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
+            _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _arr(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Context:
+    """One ``mcg_ctx``: a CUDA device, its resident contig/bin tables and a stream."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.handle = self.lib.mcg_create(int(device))
+        if not self.handle:
+            msg = self.lib.mcg_last_error(None)
+            raise McgError(ERR_CUDA, (msg or b"mcg_create failed").decode())
+        self.device = int(device)
+        self.n_contigs = 0
+        self.n_samples = 0
+        self.n_bins = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mcg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == OK:
+            return
+        msg = (self.lib.mcg_last_error(self.handle) or b"").decode()
+        if rc == ERR_DOMAIN:
+            # what the reference raises at matching_utils.py:39 when both Gaussians underflow
+            raise ZeroDivisionError("float division by zero")
+        raise McgError(rc, msg)
+
+    # -- plumbing -------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.mcg_set_stream(self.handle, cuda_stream))
+
+    def synchronize(self):
+        self._check(self.lib.mcg_synchronize(self.handle))
+
+    def profile(self, on=True):
+        self._check(self.lib.mcg_profile(self.handle, 1 if on else 0))
+
+    def timings(self):
+        ms = np.zeros(N_TIMERS, dtype=np.float32)
+        launches = _c.c_int64(0)
+        self._check(self.lib.mcg_timings(self.handle, ms.ctypes.data, _c.byref(launches)))
+        out = dict(zip(TIMER_NAMES, (float(x) for x in ms)))
+        out["launches"] = int(launches.value)
+        return out
+
+    def fp64_peak(self):
+        t = _c.c_double(0.0)
+        self._check(self.lib.mcg_fp64_peak(self.handle, _c.byref(t)))
+        return t.value
+
+    # -- featurisation ----------------------------------------------------------------
+    def tetramer_scan(self, bases, offsets, encoding=ENC_ASCII, want_counts=True, want_freqs=True):
+        bases = _arr(bases, np.uint8)
+        offsets = _arr(offsets, np.int64)
+        n = offsets.shape[0] - 1
+        counts = np.zeros((n, NPROF), dtype=np.uint32) if want_counts else None
+        freqs = np.zeros((n, NPROF), dtype=np.float64) if want_freqs else None
+        self._check(self.lib.mcg_tetramer_scan(self.handle, _ptr(bases), _ptr(offsets), n,
+                                               encoding, _ptr(counts), _ptr(freqs)))
+        self.n_contigs = n
+        return counts, freqs
+
+    def load_contigs(self, bases, offsets, encoding=ENC_ASCII):
+        bases = _arr(bases, np.uint8)
+        offsets = _arr(offsets, np.int64)
+        n = offsets.shape[0] - 1
+        self._check(self.lib.mcg_load_contigs(self.handle, _ptr(bases), _ptr(offsets), n,
+                                              encoding))
+        self.n_contigs = n
+
+    def scan(self):
+        self._check(self.lib.mcg_scan(self.handle))
+
+    def get_profiles(self, first=0, n=None, want_counts=False):
+        n = self.n_contigs - first if n is None else n
+        counts = np.zeros((n, NPROF), dtype=np.uint32) if want_counts else None
+        freqs = np.zeros((n, NPROF), dtype=np.float64)
+        self._check(self.lib.mcg_get_profiles(self.handle, first, n, _ptr(counts), _ptr(freqs)))
+        return (counts, freqs) if want_counts else freqs
+
+    def set_profiles(self, prof):
+        prof = _arr(prof, np.float64)
+        if prof.ndim != 2 or prof.shape[1] != NPROF:
+            raise ValueError("profiles must be [n,136]")
+        self._check(self.lib.mcg_set_profiles(self.handle, _ptr(prof), prof.shape[0]))
+        self.n_contigs = prof.shape[0]
+
+    def load_coverage(self, cov):
+        cov = _arr(cov, np.float64)
+        if cov.ndim != 2:
+            raise ValueError("coverage must be [n,S]")
+        self._check(self.lib.mcg_load_coverage(self.handle, _ptr(cov), cov.shape[0],
+                                               cov.shape[1]))
+        self.n_samples = cov.shape[1]
+        self._cov_rows = cov.shape[0]
+
+    def coverage_terms(self):
+        shape = (self._cov_rows, self.n_samples)
+        cov, logc, lgam = (np.zeros(shape) for _ in range(3))
+        self._check(self.lib.mcg_get_coverage_terms(self.handle, _ptr(cov), _ptr(logc),
+                                                    _ptr(lgam)))
+        return cov, logc, lgam
+
+    def bin_profiles(self, members, seg_offsets):
+        members = _arr(members, np.int64)
+        seg_offsets = _arr(seg_offsets, np.int64)
+        nseg = seg_offsets.shape[0] - 1
+        cen_prof = np.zeros((nseg, NPROF))
+        cen_cov = np.zeros((nseg, self.n_samples))
+        self._check(self.lib.mcg_bin_profiles(self.handle, _ptr(members), _ptr(seg_offsets), nseg,
+                                              _ptr(cen_prof), _ptr(cen_cov)))
+        self.n_bins = nseg
+        return cen_prof, cen_cov
+
+    # -- elementwise primitives ----------------------------------------------------------
+    def normpdf(self, x, mean, sd):
+        x = _arr(x, np.float64).reshape(-1)
+        out = np.zeros_like(x)
+        self._check(self.lib.mcg_normpdf(self.handle, _ptr(x), float(mean), float(sd), _ptr(out),
+                                         x.shape[0]))
+        return out
+
+    def tetramer_distance(self, u, v):
+        u = _arr(u, np.float64)
+        v = _arr(v, np.float64)
+        if u.ndim == 1:
+            u, v = u[None, :], v[None, :]
+        out = np.zeros(u.shape[0])
+        self._check(self.lib.mcg_tetramer_distance(self.handle, _ptr(u), _ptr(v), u.shape[0],
+                                                   u.shape[1], _ptr(out)))
+        return out
+
+    def comp_probability(self, dist):
+        dist = _arr(dist, np.float64).reshape(-1)
+        out = np.zeros_like(dist)
+        self._check(self.lib.mcg_comp_probability(self.handle, _ptr(dist), _ptr(out),
+                                                  dist.shape[0]))
+        return out
+
+    def cov_probability(self, cov1, cov2):
+        cov1 = _arr(cov1, np.float64)
+        cov2 = _arr(cov2, np.float64)
+        if cov1.ndim == 1:
+            cov1, cov2 = cov1[None, :], cov2[None, :]
+        out = np.zeros(cov1.shape[0])
+        self._check(self.lib.mcg_cov_probability(self.handle, _ptr(cov1), _ptr(cov2),
+                                                 cov1.shape[0], cov1.shape[1], _ptr(out)))
+        return out
+
+    # -- scoring ------------------------------------------------------------------------------
+    def pair_scores(self, queries, targets, want=("dist", "pc", "pv", "lp")):
+        queries = _arr(queries, np.int64)
+        targets = _arr(targets, np.int64)
+        shape = (queries.shape[0], targets.shape[0])
+        bufs = {k: (np.zeros(shape) if k in want else None) for k in ("dist", "pc", "pv", "lp")}
+        self._check(self.lib.mcg_pair_scores(self.handle, _ptr(queries), shape[0], _ptr(targets),
+                                             shape[1], _ptr(bufs["dist"]), _ptr(bufs["pc"]),
+                                             _ptr(bufs["pv"]), _ptr(bufs["lp"])))
+        return bufs
+
+    def score_centroids(self, queries=None, nq=None, cen_prof=None, cen_cov=None,
+                        want_weights=False):
+        """Rule C.  Returns (argmin int32 with -1 = None, wmin, weights or None)."""
+        if queries is not None:
+            queries = _arr(queries, np.int64)
+            nq = queries.shape[0]
+        elif nq is None:
+            nq = self.n_contigs
+        if cen_prof is not None:
+            cen_prof = _arr(cen_prof, np.float64)
+            cen_cov = _arr(cen_cov, np.float64)
+            n_bins = cen_prof.shape[0]
+            if cen_prof.shape != (n_bins, NPROF) or cen_cov.shape != (n_bins, self.n_samples):
+                raise ValueError("centroid shapes must be [B,136] and [B,S]")
+            self.n_bins = n_bins
+        n_bins = self.n_bins
+        weights = np.zeros((nq, n_bins)) if want_weights else None
+        argmin = np.zeros(nq, dtype=np.int32)
+        wmin = np.zeros(nq)
+        self._check(self.lib.mcg_score_centroids(self.handle, _ptr(queries), nq, _ptr(cen_prof),
+                                                 _ptr(cen_cov), n_bins, _ptr(weights),
+                                                 _ptr(argmin), _ptr(wmin)))
+        return argmin, wmin, weights
+
+    def score_members(self, queries, members, seg_offsets, rule):
+        queries = _arr(queries, np.int64)
+        members = _arr(members, np.int64)
+        seg_offsets = _arr(seg_offsets, np.int64)
+        nseg = seg_offsets.shape[0] - 1
+        weights = np.zeros((queries.shape[0], nseg))
+        self._check(self.lib.mcg_score_members(self.handle, _ptr(queries), queries.shape[0],
+                                               _ptr(members), _ptr(seg_offsets), nseg, int(rule),
+                                               _ptr(weights)))
+        return weights
+
+    def bfs_candidates(self, indptr, indices, labels, starts, depth_limit, max_hits=64):
+        indptr = _arr(indptr, np.int64)
+        indices = _arr(indices, np.int32)
+        labels = _arr(labels, np.int32)
+        starts = _arr(starts, np.int64)
+        n_vertices = indptr.shape[0] - 1
+        ns = starts.shape[0]
+        while True:
+            node = np.zeros((ns, max_hits), dtype=np.int32)
+            bin_ = np.zeros((ns, max_hits), dtype=np.int32)
+            depth = np.zeros((ns, max_hits), dtype=np.int32)
+            n_hits = np.zeros(ns, dtype=np.int32)
+            self._check(self.lib.mcg_bfs_candidates(
+                self.handle, _ptr(indptr), _ptr(indices), n_vertices, _ptr(labels), _ptr(starts),
+                ns, int(depth_limit), int(max_hits), _ptr(node), _ptr(bin_), _ptr(depth),
+                _ptr(n_hits)))
+            if ns == 0 or int(n_hits.max()) <= max_hits:
+                return node, bin_, depth, n_hits
+            max_hits = int(n_hits.max())
+
+    # -- fused / resident ---------------------------------------------------------------------
+    def featurise_score(self, bases, offsets, cov, cen_prof, cen_cov, encoding=ENC_ASCII,
+                        argmin=None, wmin=None):
+        offsets = _arr(offsets, np.int64)
+        n = offsets.shape[0] - 1
+        cov = _arr(cov, np.float64)
+        cen_prof = _arr(cen_prof, np.float64)
+        cen_cov = _arr(cen_cov, np.float64)
+        if argmin is None:
+            argmin = np.zeros(n, dtype=np.int32)
+        if wmin is None:
+            wmin = np.zeros(n)
+        self._check(self.lib.mcg_featurise_score(
+            self.handle, _ptr(bases), _ptr(offsets), n, encoding, _ptr(cov), cov.shape[1],
+            _ptr(cen_prof), _ptr(cen_cov), cen_prof.shape[0], _ptr(argmin), _ptr(wmin)))
+        self.n_contigs, self.n_samples, self.n_bins = n, cov.shape[1], cen_prof.shape[0]
+        self._cov_rows = n
+        return argmin, wmin
+
+    def set_centroids(self, cen_prof, cen_cov):
+        cen_prof = _arr(cen_prof, np.float64)
+        cen_cov = _arr(cen_cov, np.float64)
+        self._check(self.lib.mcg_set_centroids(self.handle, _ptr(cen_prof), _ptr(cen_cov),
+                                               cen_prof.shape[0]))
+        self.n_bins = cen_prof.shape[0]
+
+    def step_resident(self, d_argmin=None, d_wmin=None):
+        self._check(self.lib.mcg_step_resident(self.handle, d_argmin, d_wmin))
+
+    def get_assignments(self):
+        argmin = np.zeros(self.n_contigs, dtype=np.int32)
+        wmin = np.zeros(self.n_contigs)
+        self._check(self.lib.mcg_get_assignments(self.handle, _ptr(argmin), _ptr(wmin)))
+        return argmin, wmin
+
+    def synth_bases(self, offsets, genome_of, trans, seed, n_frac=1e-4, lower_frac=0.01,
+                    out=None):
+        offsets = _arr(offsets, np.int64)
+        genome_of = _arr(genome_of, np.int32)
+        trans = _arr(trans, np.float32)
+        n = offsets.shape[0] - 1
+        if out is None:
+            out = np.zeros(int(offsets[-1]), dtype=np.uint8)
+        self._check(self.lib.mcg_synth_bases(self.handle, _ptr(offsets), n, _ptr(genome_of),
+                                             _ptr(trans), trans.shape[0], int(seed),
+                                             float(n_frac), float(lower_frac), _ptr(out)))
+        return out
+
+
+def kmer_table():
+    """feature_utils.py:38-57 compute_kmer_inds(4) as a uint8[256] table."""
+    table = np.zeros(256, dtype=np.uint8)
+    rc = load_library().mcg_kmer_table(table.ctypes.data)
+    if rc != OK:
+        raise McgError(rc, "mcg_kmer_table")
+    return table
+
+
+def pinned_empty(n_bytes):
+    """A uint8 numpy array backed by page-locked memory (freed with the array)."""
+    lib = load_library()
+    p = lib.mcg_host_alloc(int(max(1, n_bytes)))
+    if not p:
+        raise MemoryError("mcg_host_alloc(%d) failed" % n_bytes)
+    buf = (_c.c_uint8 * int(max(1, n_bytes))).from_address(p)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=int(n_bytes))
+    _PINNED[p] = buf
+    import weakref
+    weakref.finalize(arr, _free_pinned, p)
+    return arr
+
+
+_PINNED = {}
+
+
+def _free_pinned(p):
+    _PINNED.pop(p, None)
+    try:
+        load_library().mcg_host_free(p)
+    except Exception:
+        pass
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device=None):
+    """Process-wide context for the drop-in modules (one per device)."""
+    if device is None:
+        device = int(os.environ.get("MCG_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        ctx = _default.get(device)
+        if ctx is None:
+            ctx = Context(device)
+            _default[device] = ctx
+        return ctx

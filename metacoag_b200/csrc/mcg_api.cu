@@ -1,0 +1,873 @@
+// C ABI of libmcg_b200.so (include/mcg_b200.h): context, staging and the host-facing entry
+// points.  The kernels live in mcg_scan.cu, mcg_score.cu and mcg_frontier.cu.
+#include <algorithm>
+#include <vector>
+
+#include "mcg_internal.cuh"
+
+// ---- errors ---------------------------------------------------------------------------
+static std::mutex g_err_mu;
+static std::string g_err;
+
+void mcg_set_global_error(const char *msg) {
+    std::lock_guard<std::mutex> lock(g_err_mu);
+    g_err = msg;
+}
+
+int mcg_fail(mcg_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    mcg_set_global_error(buf);
+    return code;
+}
+
+// ---- small helpers ----------------------------------------------------------------------
+int mcg_reserve(mcg_ctx *ctx, DevBuf &buf, size_t bytes) {
+    if (bytes <= buf.cap && buf.p) return MCG_OK;
+    if (buf.p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(buf.p);
+        buf.p = nullptr;
+        buf.cap = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&buf.p, want);
+    if (e != cudaSuccess) {
+        buf.p = nullptr;
+        return mcg_fail(ctx, MCG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want,
+                        cudaGetErrorString(e));
+    }
+    buf.cap = want;
+    return MCG_OK;
+}
+
+int mcg_pinned_reserve(mcg_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return MCG_OK;
+    if (ctx->pinned) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+    }
+    cudaError_t e = cudaMallocHost(&ctx->pinned, bytes);
+    if (e != cudaSuccess)
+        return mcg_fail(ctx, MCG_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes,
+                        cudaGetErrorString(e));
+    ctx->pinned_cap = bytes;
+    return MCG_OK;
+}
+
+void mcg_timer_begin(mcg_ctx *ctx, int slot) {
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->ev[2 * slot], ctx->stream);
+}
+
+void mcg_timer_end(mcg_ctx *ctx, int slot) {
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->ev[2 * slot + 1], ctx->stream);
+    ctx->ev_used[slot] = true;
+}
+
+int mcg_check_status(mcg_ctx *ctx) {
+    int32_t flags[4] = {0, 0, 0, 0};
+    MCG_CUDA(ctx, cudaMemcpyAsync(flags, ctx->status.p, sizeof flags, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags[0] & 1) {
+        cudaMemsetAsync(ctx->status.p, 0, sizeof flags, ctx->stream);
+        return mcg_fail(ctx, MCG_ERR_DOMAIN,
+                        "float division by zero (get_comp_probability: both Gaussians underflow)");
+    }
+    return MCG_OK;
+}
+
+static int h2d(mcg_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return MCG_OK;
+    MCG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MCG_OK;
+}
+static int d2h(mcg_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return MCG_OK;
+    MCG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return MCG_OK;
+}
+static int sync(mcg_ctx *ctx) {
+    MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCG_OK;
+}
+
+struct Guard {
+    mcg_ctx *ctx;
+    std::unique_lock<std::mutex> lock;
+    explicit Guard(mcg_ctx *c) : ctx(c), lock(c->mu) { cudaSetDevice(c->device); }
+};
+
+#define MCG_ENTER(ctx)                                   \
+    if (!(ctx)) return MCG_ERR_ARG;                      \
+    Guard guard__(ctx)
+
+// ---- context ------------------------------------------------------------------------------
+extern "C" int mcg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" mcg_ctx *mcg_create(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        mcg_set_global_error(
+            "no CUDA device: libmcg_b200 has no CPU path (cudaGetDeviceCount failed or 0)");
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        mcg_set_global_error("device index out of range");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        mcg_set_global_error("cudaSetDevice failed");
+        return nullptr;
+    }
+    mcg_ctx *ctx = new mcg_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        mcg_set_global_error("cudaStreamCreate failed");
+        delete ctx;
+        return nullptr;
+    }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 2 * MCG_N_TIMERS; ++i) cudaEventCreate(&ctx->ev[i]);
+    if (mcg_reserve(ctx, ctx->status, 4 * sizeof(int32_t)) != MCG_OK) {
+        delete ctx;
+        return nullptr;
+    }
+    cudaMemsetAsync(ctx->status.p, 0, 4 * sizeof(int32_t), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return ctx;
+}
+
+extern "C" void mcg_destroy(mcg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->packed, &ctx->meta, &ctx->seg_contig, &ctx->ascii, &ctx->offsets,
+                      &ctx->tile_counter, &ctx->counts, &ctx->prof, &ctx->cov, &ctx->logc,
+                      &ctx->lgam, &ctx->cen_prof, &ctx->cen_cov, &ctx->cen_logc, &ctx->cen_lgam,
+                      &ctx->argmin, &ctx->wmin, &ctx->status};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (DevBuf &b : ctx->scratch)
+        if (b.p) cudaFree(b.p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 2 * MCG_N_TIMERS; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *mcg_last_error(const mcg_ctx *ctx) {
+    if (ctx) return ctx->err.c_str();
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lock(g_err_mu);
+    copy = g_err;
+    return copy.c_str();
+}
+
+extern "C" int mcg_set_stream(mcg_ctx *ctx, void *cuda_stream) {
+    MCG_ENTER(ctx);
+    MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return MCG_OK;
+}
+
+extern "C" int mcg_synchronize(mcg_ctx *ctx) {
+    MCG_ENTER(ctx);
+    return sync(ctx);
+}
+
+extern "C" void *mcg_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void mcg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- canonical tetramer table (feature_utils.py:38-57) ----------------------------------------
+extern "C" int mcg_kmer_table(uint8_t table[256]) {
+    // A code and its reverse complement share a slot; slots are handed out in ascending
+    // code order (the reference walks the sorted 4-mers, which is ascending code order).
+    int slot_of[256];
+    for (int i = 0; i < 256; ++i) slot_of[i] = -1;
+    int next = 0;
+    for (int code = 0; code < 256; ++code) {
+        int rc = 0, c = code;
+        for (int i = 0; i < 4; ++i) { rc = (rc << 2) | (3 - (c & 3)); c >>= 2; }
+        if (slot_of[rc] >= 0) slot_of[code] = slot_of[rc];
+        else slot_of[code] = next++;
+        table[code] = static_cast<uint8_t>(slot_of[code]);
+    }
+    return next == MCG_NPROF ? MCG_OK : MCG_ERR_STATE;
+}
+
+// ---- contig store ---------------------------------------------------------------------------------
+// Host-side layout pass: per-contig packed word offset, first segment and window count.
+static int build_layout(mcg_ctx *ctx, const int64_t *offsets, int64_t n,
+                        std::vector<ContigMeta> &meta, int64_t *n_words, int64_t *n_seg) {
+    meta.resize(static_cast<size_t>(n));
+    int64_t words = 0, segs = 0;
+    for (int64_t c = 0; c < n; ++c) {
+        const int64_t len = offsets[c + 1] - offsets[c];
+        if (len < 0) return mcg_fail(ctx, MCG_ERR_ARG, "offsets must be non-decreasing");
+        if (len > 0x7fffff00LL) return mcg_fail(ctx, MCG_ERR_ARG, "contig longer than 2^31 bases");
+        const int64_t nwin = len >= 4 ? len - 3 : 0;
+        if (segs > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many scan segments");
+        meta[c].pk_word = words;
+        meta[c].seg_first = static_cast<int32_t>(segs);
+        meta[c].nwin = static_cast<int32_t>(nwin);
+        words += 4 * ((len + 63) / 64);
+        segs += (nwin + 255) / 256;
+    }
+    if (segs > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many scan segments");
+    *n_words = words;
+    *n_seg = segs;
+    return MCG_OK;
+}
+
+static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
+                               int64_t n, int encoding) {
+    if (n < 0 || (!offsets && n > 0)) return mcg_fail(ctx, MCG_ERR_ARG, "bad contig arguments");
+    if (encoding != MCG_ENC_ASCII && encoding != MCG_ENC_2BIT)
+        return mcg_fail(ctx, MCG_ERR_ARG, "unknown encoding %d", encoding);
+    std::vector<ContigMeta> meta;
+    int64_t n_words = 0, n_seg = 0;
+    static const int64_t zero_off[1] = {0};
+    if (n == 0) offsets = zero_off;
+    if (offsets[0] != 0) return mcg_fail(ctx, MCG_ERR_ARG, "offsets[0] must be 0");
+    MCG_TRY(build_layout(ctx, offsets, n, meta, &n_words, &n_seg));
+    const int64_t n_bases = offsets[n] - offsets[0];
+    if (n_bases > 0 && !bases) return mcg_fail(ctx, MCG_ERR_ARG, "bases is NULL");
+
+    MCG_TRY(mcg_reserve(ctx, ctx->packed, sizeof(uint32_t) * (n_words + 32)));
+    MCG_TRY(mcg_reserve(ctx, ctx->meta, sizeof(ContigMeta) * std::max<int64_t>(n, 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->seg_contig, sizeof(int32_t) * std::max<int64_t>(n_seg, 1)));
+    MCG_TRY(mcg_pinned_reserve(ctx, sizeof(ContigMeta) * std::max<int64_t>(n, 1)));
+    memcpy(ctx->pinned, meta.data(), sizeof(ContigMeta) * n);
+    {
+        TimerScope t(ctx, T_H2D);
+        MCG_TRY(h2d(ctx, ctx->meta.p, ctx->pinned, sizeof(ContigMeta) * n));
+        if (encoding == MCG_ENC_ASCII) {
+            MCG_TRY(mcg_reserve(ctx, ctx->ascii, static_cast<size_t>(n_bases) + 256));
+            MCG_TRY(mcg_reserve(ctx, ctx->offsets, sizeof(int64_t) * (n + 1)));
+            MCG_TRY(h2d(ctx, ctx->ascii.p, bases + offsets[0], static_cast<size_t>(n_bases)));
+            MCG_TRY(h2d(ctx, ctx->offsets.p, offsets, sizeof(int64_t) * (n + 1)));
+        } else {
+            MCG_TRY(h2d(ctx, ctx->packed.p, bases, sizeof(uint32_t) * n_words));
+        }
+    }
+    // the words after the last contig are read as halo / by idle lanes
+    MCG_CUDA(ctx, cudaMemsetAsync(ctx->packed.as<uint32_t>() + n_words, 0, sizeof(uint32_t) * 32,
+                                  ctx->stream));
+    if (encoding == MCG_ENC_ASCII) {
+        TimerScope t(ctx, T_PACK);
+        MCG_TRY(mcg_k_pack_ascii(ctx, ctx->ascii.as<uint8_t>(), ctx->offsets.as<int64_t>(),
+                                 ctx->meta.as<ContigMeta>(), n, n_words,
+                                 ctx->packed.as<uint32_t>()));
+    }
+    {
+        TimerScope t(ctx, T_OTHER);
+        MCG_TRY(mcg_k_fill_seg_contig(ctx, ctx->meta.as<ContigMeta>(), n, n_seg,
+                                      ctx->seg_contig.as<int32_t>()));
+    }
+    // the pinned meta block must not be overwritten before the copy has left
+    MCG_TRY(sync(ctx));
+    ctx->n_contigs = n;
+    ctx->n_words = n_words;
+    ctx->n_seg = n_seg;
+    ctx->n_bases = n_bases;
+    return MCG_OK;
+}
+
+static int scan_locked(mcg_ctx *ctx) {
+    const int64_t n = ctx->n_contigs;
+    MCG_TRY(mcg_reserve(ctx, ctx->counts, sizeof(uint32_t) * MCG_NPROF * std::max<int64_t>(n, 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->prof, sizeof(double) * MCG_NPROF * std::max<int64_t>(n, 1)));
+    {
+        TimerScope t(ctx, T_SCAN);
+        MCG_TRY(mcg_k_scan(ctx, ctx->packed.as<uint32_t>(), ctx->meta.as<ContigMeta>(),
+                           ctx->seg_contig.as<int32_t>(), ctx->n_seg, n,
+                           ctx->counts.as<uint32_t>()));
+    }
+    {
+        TimerScope t(ctx, T_NORM);
+        MCG_TRY(mcg_k_normalise(ctx, ctx->counts.as<uint32_t>(), ctx->meta.as<ContigMeta>(), n,
+                                ctx->prof.as<double>()));
+    }
+    ctx->n_prof = n;
+    return MCG_OK;
+}
+
+extern "C" int mcg_load_contigs(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
+                                int64_t n, int encoding) {
+    MCG_ENTER(ctx);
+    return load_contigs_locked(ctx, bases, offsets, n, encoding);
+}
+
+extern "C" int mcg_scan(mcg_ctx *ctx) {
+    MCG_ENTER(ctx);
+    return scan_locked(ctx);
+}
+
+static int get_profiles_locked(mcg_ctx *ctx, int64_t first, int64_t n, uint32_t *counts,
+                               double *freqs) {
+    if (first < 0 || n < 0 || first + n > ctx->n_prof)
+        return mcg_fail(ctx, MCG_ERR_ARG, "profile range [%lld,%lld) outside 0..%lld",
+                        (long long)first, (long long)(first + n), (long long)ctx->n_prof);
+    TimerScope t(ctx, T_D2H);
+    if (counts) {
+        if (!ctx->counts.p || ctx->n_contigs != ctx->n_prof)
+            return mcg_fail(ctx, MCG_ERR_STATE, "no scan counts resident");
+        MCG_TRY(d2h(ctx, counts, ctx->counts.as<uint32_t>() + first * MCG_NPROF,
+                    sizeof(uint32_t) * MCG_NPROF * n));
+    }
+    if (freqs)
+        MCG_TRY(d2h(ctx, freqs, ctx->prof.as<double>() + first * MCG_NPROF,
+                    sizeof(double) * MCG_NPROF * n));
+    return sync(ctx);
+}
+
+extern "C" int mcg_get_profiles(mcg_ctx *ctx, int64_t first, int64_t n, uint32_t *counts,
+                                double *freqs) {
+    MCG_ENTER(ctx);
+    return get_profiles_locked(ctx, first, n, counts, freqs);
+}
+
+extern "C" int mcg_tetramer_scan(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
+                                 int64_t n, int encoding, uint32_t *counts, double *freqs) {
+    MCG_ENTER(ctx);
+    MCG_TRY(load_contigs_locked(ctx, bases, offsets, n, encoding));
+    MCG_TRY(scan_locked(ctx));
+    return get_profiles_locked(ctx, 0, n, counts, freqs);
+}
+
+extern "C" int mcg_set_profiles(mcg_ctx *ctx, const double *prof, int64_t n) {
+    MCG_ENTER(ctx);
+    if (n < 0 || (n > 0 && !prof)) return mcg_fail(ctx, MCG_ERR_ARG, "bad profile arguments");
+    MCG_TRY(mcg_reserve(ctx, ctx->prof, sizeof(double) * MCG_NPROF * std::max<int64_t>(n, 1)));
+    MCG_TRY(h2d(ctx, ctx->prof.p, prof, sizeof(double) * MCG_NPROF * n));
+    MCG_TRY(sync(ctx));
+    ctx->n_prof = n;
+    return MCG_OK;
+}
+
+// ---- coverage -----------------------------------------------------------------------------------------
+static int load_coverage_locked(mcg_ctx *ctx, const double *cov, int64_t n, int S) {
+    if (n < 0 || S <= 0 || (n > 0 && !cov)) return mcg_fail(ctx, MCG_ERR_ARG, "bad coverage arguments");
+    const size_t bytes = sizeof(double) * static_cast<size_t>(std::max<int64_t>(n, 1)) * S;
+    MCG_TRY(mcg_reserve(ctx, ctx->cov, bytes));
+    MCG_TRY(mcg_reserve(ctx, ctx->logc, bytes));
+    MCG_TRY(mcg_reserve(ctx, ctx->lgam, bytes));
+    {
+        TimerScope t(ctx, T_H2D);
+        MCG_TRY(h2d(ctx, ctx->cov.p, cov, sizeof(double) * n * S));
+    }
+    ctx->n_cov = n;
+    ctx->n_samples = S;
+    return MCG_OK;
+}
+
+static int cov_terms_locked(mcg_ctx *ctx) {
+    TimerScope t(ctx, T_COV);
+    return mcg_k_cov_terms(ctx, ctx->cov.as<double>(), ctx->logc.as<double>(),
+                           ctx->lgam.as<double>(), ctx->n_cov * ctx->n_samples);
+}
+
+extern "C" int mcg_load_coverage(mcg_ctx *ctx, const double *cov, int64_t n, int n_samples) {
+    MCG_ENTER(ctx);
+    MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples));
+    MCG_TRY(cov_terms_locked(ctx));
+    return sync(ctx);
+}
+
+extern "C" int mcg_get_coverage_terms(mcg_ctx *ctx, double *cov, double *logc, double *lgam) {
+    MCG_ENTER(ctx);
+    const size_t bytes = sizeof(double) * ctx->n_cov * ctx->n_samples;
+    if (cov) MCG_TRY(d2h(ctx, cov, ctx->cov.p, bytes));
+    if (logc) MCG_TRY(d2h(ctx, logc, ctx->logc.p, bytes));
+    if (lgam) MCG_TRY(d2h(ctx, lgam, ctx->lgam.p, bytes));
+    return sync(ctx);
+}
+
+// ---- bin tables ------------------------------------------------------------------------------------------
+static int need_features(mcg_ctx *ctx) {
+    if (ctx->n_prof == 0 || !ctx->prof.p)
+        return mcg_fail(ctx, MCG_ERR_STATE, "no profiles resident (mcg_scan / mcg_set_profiles)");
+    if (ctx->n_cov == 0 || !ctx->cov.p)
+        return mcg_fail(ctx, MCG_ERR_STATE, "no coverage resident (mcg_load_coverage)");
+    return MCG_OK;
+}
+
+static int check_ids(mcg_ctx *ctx, const int64_t *ids, int64_t n, int64_t limit, const char *what) {
+    for (int64_t i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= limit)
+            return mcg_fail(ctx, MCG_ERR_ARG, "%s[%lld] = %lld outside 0..%lld", what, (long long)i,
+                            (long long)ids[i], (long long)limit);
+    return MCG_OK;
+}
+
+static int set_centroids_locked(mcg_ctx *ctx, const double *cen_prof, const double *cen_cov,
+                                int64_t B, int S) {
+    if (B <= 0 || !cen_prof || !cen_cov) return mcg_fail(ctx, MCG_ERR_ARG, "bad centroid arguments");
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_prof, sizeof(double) * MCG_NPROF * B));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_cov, sizeof(double) * S * B));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_logc, sizeof(double) * S * B));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_lgam, sizeof(double) * S * B));
+    {
+        TimerScope t(ctx, T_H2D);
+        MCG_TRY(h2d(ctx, ctx->cen_prof.p, cen_prof, sizeof(double) * MCG_NPROF * B));
+        MCG_TRY(h2d(ctx, ctx->cen_cov.p, cen_cov, sizeof(double) * S * B));
+    }
+    // centroid coverages are means of clamped values, so the clamp in the kernel is inert
+    MCG_TRY(mcg_k_cov_terms(ctx, ctx->cen_cov.as<double>(), ctx->cen_logc.as<double>(),
+                            ctx->cen_lgam.as<double>(), B * S));
+    ctx->n_bins = B;
+    ctx->cen_samples = S;
+    return MCG_OK;
+}
+
+extern "C" int mcg_set_centroids(mcg_ctx *ctx, const double *cen_prof, const double *cen_cov,
+                                 int64_t n_bins) {
+    MCG_ENTER(ctx);
+    if (ctx->n_samples <= 0) return mcg_fail(ctx, MCG_ERR_STATE, "load coverage before centroids");
+    MCG_TRY(set_centroids_locked(ctx, cen_prof, cen_cov, n_bins, ctx->n_samples));
+    return sync(ctx);
+}
+
+extern "C" int mcg_bin_profiles(mcg_ctx *ctx, const int64_t *members, const int64_t *seg_offsets,
+                                int64_t nseg, double *cen_prof, double *cen_cov) {
+    MCG_ENTER(ctx);
+    MCG_TRY(need_features(ctx));
+    if (nseg <= 0 || !seg_offsets) return mcg_fail(ctx, MCG_ERR_ARG, "bad segment arguments");
+    const int64_t nm = seg_offsets[nseg];
+    if (seg_offsets[0] != 0) return mcg_fail(ctx, MCG_ERR_ARG, "seg_offsets[0] must be 0");
+    for (int64_t b = 0; b < nseg; ++b)
+        if (seg_offsets[b + 1] <= seg_offsets[b])
+            return mcg_fail(ctx, MCG_ERR_ARG, "bin %lld has no members", (long long)b);
+    MCG_TRY(check_ids(ctx, members, nm, std::min(ctx->n_prof, ctx->n_cov), "members"));
+    const int S = ctx->n_samples;
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(int64_t) * nm));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(int64_t) * (nseg + 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_prof, sizeof(double) * MCG_NPROF * nseg));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_cov, sizeof(double) * S * nseg));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_logc, sizeof(double) * S * nseg));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_lgam, sizeof(double) * S * nseg));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, members, sizeof(int64_t) * nm));
+    MCG_TRY(h2d(ctx, ctx->scratch[1].p, seg_offsets, sizeof(int64_t) * (nseg + 1)));
+    MCG_TRY(mcg_k_segment_mean(ctx, ctx->prof.as<double>(), MCG_NPROF,
+                               ctx->scratch[0].as<int64_t>(), ctx->scratch[1].as<int64_t>(), nseg,
+                               ctx->cen_prof.as<double>()));
+    MCG_TRY(mcg_k_segment_mean(ctx, ctx->cov.as<double>(), S, ctx->scratch[0].as<int64_t>(),
+                               ctx->scratch[1].as<int64_t>(), nseg, ctx->cen_cov.as<double>()));
+    if (cen_prof) MCG_TRY(d2h(ctx, cen_prof, ctx->cen_prof.p, sizeof(double) * MCG_NPROF * nseg));
+    if (cen_cov) MCG_TRY(d2h(ctx, cen_cov, ctx->cen_cov.p, sizeof(double) * S * nseg));
+    MCG_TRY(mcg_k_cov_terms(ctx, ctx->cen_cov.as<double>(), ctx->cen_logc.as<double>(),
+                            ctx->cen_lgam.as<double>(), nseg * S));
+    ctx->n_bins = nseg;
+    ctx->cen_samples = S;
+    return sync(ctx);
+}
+
+// ---- elementwise primitives ----------------------------------------------------------------------------------
+extern "C" int mcg_normpdf(mcg_ctx *ctx, const double *x, double mean, double sd, double *out,
+                           int64_t n) {
+    MCG_ENTER(ctx);
+    if (n < 0 || (n > 0 && (!x || !out))) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(double) * n));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(double) * n));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, x, sizeof(double) * n));
+    MCG_TRY(mcg_k_normpdf(ctx, ctx->scratch[0].as<double>(), mean, sd,
+                          ctx->scratch[1].as<double>(), n));
+    MCG_TRY(d2h(ctx, out, ctx->scratch[1].p, sizeof(double) * n));
+    return sync(ctx);
+}
+
+extern "C" int mcg_tetramer_distance(mcg_ctx *ctx, const double *u, const double *v, int64_t n,
+                                     int width, double *out) {
+    MCG_ENTER(ctx);
+    if (n < 0 || width <= 0 || (n > 0 && (!u || !v || !out)))
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    const size_t bytes = sizeof(double) * n * width;
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], bytes));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], bytes));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[2], sizeof(double) * n));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, u, bytes));
+    MCG_TRY(h2d(ctx, ctx->scratch[1].p, v, bytes));
+    MCG_TRY(mcg_k_distance(ctx, ctx->scratch[0].as<double>(), ctx->scratch[1].as<double>(), n,
+                           width, ctx->scratch[2].as<double>()));
+    MCG_TRY(d2h(ctx, out, ctx->scratch[2].p, sizeof(double) * n));
+    return sync(ctx);
+}
+
+extern "C" int mcg_comp_probability(mcg_ctx *ctx, const double *dist, double *out, int64_t n) {
+    MCG_ENTER(ctx);
+    if (n < 0 || (n > 0 && (!dist || !out))) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(double) * n));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(double) * n));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, dist, sizeof(double) * n));
+    MCG_TRY(mcg_k_comp_prob(ctx, ctx->scratch[0].as<double>(), ctx->scratch[1].as<double>(), n,
+                            ctx->status.as<int32_t>()));
+    MCG_TRY(d2h(ctx, out, ctx->scratch[1].p, sizeof(double) * n));
+    return mcg_check_status(ctx);
+}
+
+extern "C" int mcg_cov_probability(mcg_ctx *ctx, const double *cov1, const double *cov2, int64_t n,
+                                   int n_samples, double *out) {
+    MCG_ENTER(ctx);
+    if (n < 0 || n_samples <= 0 || (n > 0 && (!cov1 || !cov2 || !out)))
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    const size_t bytes = sizeof(double) * n * n_samples;
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], bytes));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], bytes));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[2], sizeof(double) * n));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, cov1, bytes));
+    MCG_TRY(h2d(ctx, ctx->scratch[1].p, cov2, bytes));
+    MCG_TRY(mcg_k_cov_prob(ctx, ctx->scratch[0].as<double>(), ctx->scratch[1].as<double>(), n,
+                           n_samples, ctx->scratch[2].as<double>()));
+    MCG_TRY(d2h(ctx, out, ctx->scratch[2].p, sizeof(double) * n));
+    return sync(ctx);
+}
+
+// ---- scoring -----------------------------------------------------------------------------------------------------
+static ScoreSide contig_side(mcg_ctx *ctx, const int64_t *d_index, int64_t n) {
+    ScoreSide s;
+    s.prof = ctx->prof.as<double>();
+    s.cov = ctx->cov.as<double>();
+    s.logc = ctx->logc.as<double>();
+    s.lgam = ctx->lgam.as<double>();
+    s.index = d_index;
+    s.n = n;
+    return s;
+}
+
+static ScoreSide centroid_side(mcg_ctx *ctx) {
+    ScoreSide s;
+    s.prof = ctx->cen_prof.as<double>();
+    s.cov = ctx->cen_cov.as<double>();
+    s.logc = ctx->cen_logc.as<double>();
+    s.lgam = ctx->cen_lgam.as<double>();
+    s.index = nullptr;
+    s.n = ctx->n_bins;
+    return s;
+}
+
+extern "C" int mcg_pair_scores(mcg_ctx *ctx, const int64_t *queries, int64_t nq,
+                               const int64_t *targets, int64_t nt, double *dist, double *pc,
+                               double *pv, double *lp) {
+    MCG_ENTER(ctx);
+    MCG_TRY(need_features(ctx));
+    if (nq <= 0 || nt <= 0 || !queries || !targets) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    const int64_t limit = std::min(ctx->n_prof, ctx->n_cov);
+    MCG_TRY(check_ids(ctx, queries, nq, limit, "queries"));
+    MCG_TRY(check_ids(ctx, targets, nt, limit, "targets"));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(int64_t) * nq));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(int64_t) * nt));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, queries, sizeof(int64_t) * nq));
+    MCG_TRY(h2d(ctx, ctx->scratch[1].p, targets, sizeof(int64_t) * nt));
+    const size_t mat = sizeof(double) * nq * nt;
+    double *host[4] = {dist, pc, pv, lp};
+    double *dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; ++i)
+        if (host[i]) {
+            MCG_TRY(mcg_reserve(ctx, ctx->scratch[2 + i], mat));
+            dev[i] = ctx->scratch[2 + i].as<double>();
+        }
+    ScoreOut out;
+    out.dist = dev[0]; out.pc = dev[1]; out.pv = dev[2]; out.lp = dev[3];
+    {
+        TimerScope t(ctx, T_SCORE);
+        MCG_TRY(mcg_k_pairs(ctx, contig_side(ctx, ctx->scratch[0].as<int64_t>(), nq),
+                            contig_side(ctx, ctx->scratch[1].as<int64_t>(), nt), ctx->n_samples,
+                            out, ctx->status.as<int32_t>()));
+    }
+    for (int i = 0; i < 4; ++i)
+        if (host[i]) MCG_TRY(d2h(ctx, host[i], dev[i], mat));
+    // a NaN prob_comp is reported in pc; the caller decides whether it is an error
+    MCG_TRY(sync(ctx));
+    cudaMemsetAsync(ctx->status.p, 0, 4 * sizeof(int32_t), ctx->stream);
+    return MCG_OK;
+}
+
+static int score_centroids_locked(mcg_ctx *ctx, const int64_t *d_queries, int64_t nq,
+                                  double *d_weights, int32_t *d_argmin, double *d_wmin) {
+    ScoreOut out;
+    out.weights = d_weights;
+    out.argmin = d_argmin;
+    out.wmin = d_wmin;
+    TimerScope t(ctx, T_SCORE);
+    return mcg_k_pairs(ctx, contig_side(ctx, d_queries, nq), centroid_side(ctx), ctx->n_samples,
+                       out, ctx->status.as<int32_t>());
+}
+
+extern "C" int mcg_score_centroids(mcg_ctx *ctx, const int64_t *queries, int64_t nq,
+                                   const double *cen_prof, const double *cen_cov, int64_t n_bins,
+                                   double *weights, int32_t *argmin, double *wmin) {
+    MCG_ENTER(ctx);
+    MCG_TRY(need_features(ctx));
+    if (nq < 0) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    const int64_t limit = std::min(ctx->n_prof, ctx->n_cov);
+    if (cen_prof || cen_cov) {
+        MCG_TRY(set_centroids_locked(ctx, cen_prof, cen_cov, n_bins, ctx->n_samples));
+    } else if (ctx->n_bins == 0) {
+        return mcg_fail(ctx, MCG_ERR_STATE, "no centroids resident");
+    }
+    if (nq == 0) return MCG_OK;
+    const int64_t *d_queries = nullptr;
+    if (queries) {
+        MCG_TRY(check_ids(ctx, queries, nq, limit, "queries"));
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(int64_t) * nq));
+        MCG_TRY(h2d(ctx, ctx->scratch[0].p, queries, sizeof(int64_t) * nq));
+        d_queries = ctx->scratch[0].as<int64_t>();
+    } else if (nq > limit) {
+        return mcg_fail(ctx, MCG_ERR_ARG, "nq exceeds the resident contig table");
+    }
+    const int64_t B = ctx->n_bins;
+    MCG_TRY(mcg_reserve(ctx, ctx->argmin, sizeof(int32_t) * nq));
+    MCG_TRY(mcg_reserve(ctx, ctx->wmin, sizeof(double) * nq));
+    double *d_weights = nullptr;
+    if (weights) {
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[2], sizeof(double) * nq * B));
+        d_weights = ctx->scratch[2].as<double>();
+    }
+    MCG_TRY(score_centroids_locked(ctx, d_queries, nq, d_weights, ctx->argmin.as<int32_t>(),
+                                   ctx->wmin.as<double>()));
+    {
+        TimerScope t(ctx, T_D2H);
+        if (weights) MCG_TRY(d2h(ctx, weights, d_weights, sizeof(double) * nq * B));
+        if (argmin) MCG_TRY(d2h(ctx, argmin, ctx->argmin.p, sizeof(int32_t) * nq));
+        if (wmin) MCG_TRY(d2h(ctx, wmin, ctx->wmin.p, sizeof(double) * nq));
+    }
+    return mcg_check_status(ctx);
+}
+
+extern "C" int mcg_score_members(mcg_ctx *ctx, const int64_t *queries, int64_t nq,
+                                 const int64_t *members, const int64_t *seg_offsets, int64_t nseg,
+                                 int rule, double *weights) {
+    MCG_ENTER(ctx);
+    MCG_TRY(need_features(ctx));
+    if (nq < 0 || nseg < 0 || !seg_offsets || !weights || (rule != MCG_RULE_A && rule != MCG_RULE_B))
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    if (nq == 0 || nseg == 0) return MCG_OK;
+    const int64_t nm = seg_offsets[nseg];
+    const int64_t limit = std::min(ctx->n_prof, ctx->n_cov);
+    MCG_TRY(check_ids(ctx, queries, nq, limit, "queries"));
+    MCG_TRY(check_ids(ctx, members, nm, limit, "members"));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(int64_t) * nq));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(int64_t) * std::max<int64_t>(nm, 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[2], sizeof(int64_t) * (nseg + 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[3], sizeof(double) * nq * std::max<int64_t>(nm, 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[4], sizeof(double) * nq * nseg));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, queries, sizeof(int64_t) * nq));
+    MCG_TRY(h2d(ctx, ctx->scratch[1].p, members, sizeof(int64_t) * nm));
+    MCG_TRY(h2d(ctx, ctx->scratch[2].p, seg_offsets, sizeof(int64_t) * (nseg + 1)));
+    {
+        TimerScope t(ctx, T_SCORE);
+        if (nm > 0) {
+            ScoreOut out;
+            out.lp = ctx->scratch[3].as<double>();
+            MCG_TRY(mcg_k_pairs(ctx, contig_side(ctx, ctx->scratch[0].as<int64_t>(), nq),
+                                contig_side(ctx, ctx->scratch[1].as<int64_t>(), nm),
+                                ctx->n_samples, out, ctx->status.as<int32_t>()));
+        }
+        MCG_TRY(mcg_k_aggregate_members(ctx, ctx->scratch[3].as<double>(), nq, nm,
+                                        ctx->scratch[2].as<int64_t>(), nseg, rule,
+                                        ctx->scratch[4].as<double>()));
+    }
+    MCG_TRY(d2h(ctx, weights, ctx->scratch[4].p, sizeof(double) * nq * nseg));
+    return mcg_check_status(ctx);
+}
+
+// ---- frontier ---------------------------------------------------------------------------------------------------------
+extern "C" int mcg_bfs_candidates(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
+                                  int64_t n_vertices, const int32_t *labels, const int64_t *starts,
+                                  int64_t n_starts, int depth_limit, int max_hits_per_node,
+                                  int32_t *hit_node, int32_t *hit_bin, int32_t *hit_depth,
+                                  int32_t *n_hits) {
+    MCG_ENTER(ctx);
+    if (n_vertices <= 0 || n_starts < 0 || !indptr || !labels || max_hits_per_node <= 0)
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    if (n_starts == 0) return MCG_OK;
+    MCG_TRY(check_ids(ctx, starts, n_starts, n_vertices, "starts"));
+    const int64_t n_edges = indptr[n_vertices];
+    DevBuf d_indptr, d_indices, d_labels, d_starts, d_hits, d_nhits, d_work;
+    int rc = MCG_OK;
+    int64_t work_stride = 1024;
+    auto cleanup = [&]() {
+        for (DevBuf *b : {&d_indptr, &d_indices, &d_labels, &d_starts, &d_hits, &d_nhits, &d_work})
+            if (b->p) cudaFree(b->p);
+    };
+#define BFS_TRY(expr) do { rc = (expr); if (rc != MCG_OK) { cleanup(); return rc; } } while (0)
+    BFS_TRY(mcg_reserve(ctx, d_indptr, sizeof(int64_t) * (n_vertices + 1)));
+    BFS_TRY(mcg_reserve(ctx, d_indices, sizeof(int32_t) * std::max<int64_t>(n_edges, 1)));
+    BFS_TRY(mcg_reserve(ctx, d_labels, sizeof(int32_t) * n_vertices));
+    BFS_TRY(mcg_reserve(ctx, d_starts, sizeof(int64_t) * n_starts));
+    BFS_TRY(mcg_reserve(ctx, d_hits, sizeof(int32_t) * 3 * n_starts * max_hits_per_node));
+    BFS_TRY(mcg_reserve(ctx, d_nhits, sizeof(int32_t) * n_starts));
+    BFS_TRY(h2d(ctx, d_indptr.p, indptr, sizeof(int64_t) * (n_vertices + 1)));
+    BFS_TRY(h2d(ctx, d_indices.p, indices, sizeof(int32_t) * n_edges));
+    BFS_TRY(h2d(ctx, d_labels.p, labels, sizeof(int32_t) * n_vertices));
+    BFS_TRY(h2d(ctx, d_starts.p, starts, sizeof(int64_t) * n_starts));
+    int32_t *hn = d_hits.as<int32_t>();
+    int32_t *hb = hn + n_starts * max_hits_per_node;
+    int32_t *hd = hb + n_starts * max_hits_per_node;
+    std::vector<int32_t> counts(static_cast<size_t>(n_starts));
+    for (;;) {
+        // the per-start slice grows until no walk overflows its queue / table
+        if (d_work.p) { cudaFree(d_work.p); d_work = DevBuf(); }
+        BFS_TRY(mcg_reserve(ctx, d_work, sizeof(int32_t) * work_stride * n_starts));
+        BFS_TRY(mcg_k_bfs(ctx, d_indptr.as<int64_t>(), d_indices.as<int32_t>(), n_vertices,
+                          d_labels.as<int32_t>(), d_starts.as<int64_t>(), n_starts, depth_limit,
+                          max_hits_per_node, hn, hb, hd, d_nhits.as<int32_t>(),
+                          d_work.as<int32_t>(), work_stride));
+        BFS_TRY(d2h(ctx, counts.data(), d_nhits.p, sizeof(int32_t) * n_starts));
+        BFS_TRY(sync(ctx));
+        bool overflow = false;
+        for (int64_t i = 0; i < n_starts; ++i) overflow |= counts[i] == -2;
+        if (!overflow) break;
+        work_stride *= 4;
+        if (sizeof(int32_t) * work_stride * n_starts > (size_t(8) << 30)) {
+            cleanup();
+            return mcg_fail(ctx, MCG_ERR_NOMEM, "BFS work buffer would exceed 8 GiB");
+        }
+    }
+    const size_t hb_bytes = sizeof(int32_t) * n_starts * max_hits_per_node;
+    if (hit_node) BFS_TRY(d2h(ctx, hit_node, hn, hb_bytes));
+    if (hit_bin) BFS_TRY(d2h(ctx, hit_bin, hb, hb_bytes));
+    if (hit_depth) BFS_TRY(d2h(ctx, hit_depth, hd, hb_bytes));
+    BFS_TRY(sync(ctx));
+    if (n_hits) memcpy(n_hits, counts.data(), sizeof(int32_t) * n_starts);
+    cleanup();
+#undef BFS_TRY
+    return MCG_OK;
+}
+
+// ---- fused plug-in call and the resident step ---------------------------------------------------------------------------
+static int step_locked(mcg_ctx *ctx, int32_t *d_argmin, double *d_wmin) {
+    if (ctx->n_contigs == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no contigs resident");
+    if (ctx->n_cov != ctx->n_contigs)
+        return mcg_fail(ctx, MCG_ERR_STATE, "coverage rows (%lld) != contigs (%lld)",
+                        (long long)ctx->n_cov, (long long)ctx->n_contigs);
+    if (ctx->n_bins == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no centroids resident");
+    MCG_TRY(scan_locked(ctx));
+    MCG_TRY(cov_terms_locked(ctx));
+    const int64_t n = ctx->n_contigs;
+    if (!d_argmin) {
+        MCG_TRY(mcg_reserve(ctx, ctx->argmin, sizeof(int32_t) * n));
+        d_argmin = ctx->argmin.as<int32_t>();
+    }
+    if (!d_wmin) {
+        MCG_TRY(mcg_reserve(ctx, ctx->wmin, sizeof(double) * n));
+        d_wmin = ctx->wmin.as<double>();
+    }
+    return score_centroids_locked(ctx, nullptr, n, nullptr, d_argmin, d_wmin);
+}
+
+extern "C" int mcg_step_resident(mcg_ctx *ctx, void *d_argmin, void *d_wmin) {
+    MCG_ENTER(ctx);
+    return step_locked(ctx, static_cast<int32_t *>(d_argmin), static_cast<double *>(d_wmin));
+}
+
+extern "C" int mcg_get_assignments(mcg_ctx *ctx, int32_t *argmin, double *wmin) {
+    MCG_ENTER(ctx);
+    const int64_t n = ctx->n_contigs;
+    {
+        TimerScope t(ctx, T_D2H);
+        if (argmin) MCG_TRY(d2h(ctx, argmin, ctx->argmin.p, sizeof(int32_t) * n));
+        if (wmin) MCG_TRY(d2h(ctx, wmin, ctx->wmin.p, sizeof(double) * n));
+    }
+    return mcg_check_status(ctx);
+}
+
+extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
+                                   int64_t n, int encoding, const double *cov, int n_samples,
+                                   const double *cen_prof, const double *cen_cov, int64_t n_bins,
+                                   int32_t *argmin, double *wmin) {
+    MCG_ENTER(ctx);
+    if (n <= 0) return mcg_fail(ctx, MCG_ERR_ARG, "no contigs");
+    MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples));
+    MCG_TRY(set_centroids_locked(ctx, cen_prof, cen_cov, n_bins, n_samples));
+    MCG_TRY(load_contigs_locked(ctx, bases, offsets, n, encoding));
+    MCG_TRY(step_locked(ctx, nullptr, nullptr));
+    {
+        TimerScope t(ctx, T_D2H);
+        if (argmin) MCG_TRY(d2h(ctx, argmin, ctx->argmin.p, sizeof(int32_t) * n));
+        if (wmin) MCG_TRY(d2h(ctx, wmin, ctx->wmin.p, sizeof(double) * n));
+    }
+    return mcg_check_status(ctx);
+}
+
+// ---- timing -------------------------------------------------------------------------------------------------------------------
+extern "C" int mcg_profile(mcg_ctx *ctx, int on) {
+    MCG_ENTER(ctx);
+    ctx->profiling = on != 0;
+    ctx->launches = 0;
+    for (int i = 0; i < MCG_N_TIMERS; ++i) { ctx->ev_used[i] = false; ctx->ms[i] = 0.f; }
+    return MCG_OK;
+}
+
+extern "C" int mcg_timings(mcg_ctx *ctx, float *ms, int64_t *launches) {
+    MCG_ENTER(ctx);
+    MCG_TRY(sync(ctx));
+    for (int i = 0; i < MCG_N_TIMERS; ++i) {
+        float t = 0.f;
+        if (ctx->ev_used[i]) cudaEventElapsedTime(&t, ctx->ev[2 * i], ctx->ev[2 * i + 1]);
+        if (ms) ms[i] = t;
+        ctx->ev_used[i] = false;
+    }
+    if (launches) *launches = ctx->launches;
+    ctx->launches = 0;
+    return MCG_OK;
+}
+
+// ---- synthetic data / peak -----------------------------------------------------------------------------------------------------
+extern "C" int mcg_synth_bases(mcg_ctx *ctx, const int64_t *offsets, int64_t n,
+                               const int32_t *genome_of, const float *trans, int n_genomes,
+                               uint64_t seed, double n_frac, double lower_frac, uint8_t *bases) {
+    MCG_ENTER(ctx);
+    if (n <= 0 || !offsets || !genome_of || !trans || n_genomes <= 0 || !bases || offsets[0] != 0)
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    for (int64_t i = 0; i < n; ++i)
+        if (genome_of[i] < 0 || genome_of[i] >= n_genomes)
+            return mcg_fail(ctx, MCG_ERR_ARG, "genome_of[%lld] out of range", (long long)i);
+    const int64_t n_bases = offsets[n];
+    MCG_TRY(mcg_reserve(ctx, ctx->ascii, static_cast<size_t>(n_bases) + 256));
+    MCG_TRY(mcg_reserve(ctx, ctx->offsets, sizeof(int64_t) * (n + 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(int32_t) * n));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(float) * 16 * n_genomes));
+    MCG_TRY(h2d(ctx, ctx->offsets.p, offsets, sizeof(int64_t) * (n + 1)));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, genome_of, sizeof(int32_t) * n));
+    MCG_TRY(h2d(ctx, ctx->scratch[1].p, trans, sizeof(float) * 16 * n_genomes));
+    MCG_TRY(mcg_k_synth(ctx, ctx->offsets.as<int64_t>(), n, ctx->scratch[0].as<int32_t>(),
+                        ctx->scratch[1].as<float>(), seed, n_frac, lower_frac,
+                        ctx->ascii.as<uint8_t>(), n_bases));
+    MCG_TRY(d2h(ctx, bases, ctx->ascii.p, static_cast<size_t>(n_bases)));
+    return sync(ctx);
+}
+
+extern "C" int mcg_fp64_peak(mcg_ctx *ctx, double *tflops) {
+    MCG_ENTER(ctx);
+    if (!tflops) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    return mcg_k_fp64_peak(ctx, tflops);
+}

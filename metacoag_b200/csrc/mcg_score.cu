@@ -1,0 +1,562 @@
+// Coverage featurisation, bin profiles and the composition x coverage scoring kernels
+// (SURVEY.md section 8a rows 5-12).
+//
+//   reference arithmetic: matching_utils.py:21-66 (normpdf, get_tetramer_distance,
+//   get_comp_probability, get_cov_probability), the aggregation rules of
+//   matching_utils.py:117-155 / 368-398 (A), label_prop_utils.py:54-86 (B) and
+//   label_prop_utils.py:308-345 (C), feature_utils.py:217-235 (get_bin_profiles).
+//
+// Everything is float64 on the CUDA cores (the reference is float64, K = 136 is small,
+// and parity is 1e-9 relative on the probabilities), so the roofline is the FP64 pipe.
+//
+// pair_kernel: a CTA owns a 64-row tile of the "A" side (contigs to score) and walks the
+// "B" side (bin centroids, or member contigs for rules A/B) in 64-row tiles.  Both tiles
+// are staged in shared memory transposed ([k][row], XOR-swizzled so that the transposing
+// store and the strided reads are both conflict-free); each of the 256 threads owns a
+// 4 x 4 block of pairs (rows ti+16e, columns tj+16f), so every shared-memory operand is
+// reused four times from registers.  The Poisson product over samples is kept strictly
+// in sample order per pair (the reference's running product decides the
+// prob_product > 0 branch through underflow), with log(c) and lgamma(c+1) hoisted per
+// (row, sample) by cov_terms_kernel.
+#include "mcg_internal.cuh"
+
+namespace {
+
+constexpr int kTile = 64;          // rows per side per CTA tile
+constexpr int kPairThreads = 256;
+constexpr int kSampleChunk = 16;   // samples staged per pass
+constexpr size_t kPairSmem =
+    sizeof(double) * (2 * MCG_NPROF * kTile + 2 * kSampleChunk * 3 * kTile);
+
+// matching_utils.py:12-15
+struct GaussConst {
+    double two_var_intra, denom_intra;   // 2*sd^2, sd*sqrt(2*pi)
+    double mu_inter, two_var_inter, denom_inter;
+    double ln10;
+};
+__constant__ GaussConst c_gauss;
+
+// ---- CPython's math.lgamma for x > 0 (Modules/mathmodule.c: Lanczos approximation with
+// the lanczos13m53 rational, g = 6.024680040776729583740234375), restated; the operation
+// order is the one oracle/mcg_oracle.c pins against math.lgamma. ---------------------------
+__constant__ double c_lanczos_num[13] = {
+    23531376880.410759688572007674451636754734846804940,
+    42919803642.649098768957899047001988850926355848959,
+    35711959237.355668049440185451547166705960488635843,
+    17921034426.037209699919755754458931112671403265390,
+    6039542586.3520280050642916443072979210699388420708,
+    1439720407.3117216736632230727949123939715485786772,
+    248874557.86205415651146038641322942321632125127801,
+    31426415.585400194380614231628318205362874684987640,
+    2876370.6289353724412254090516208496135991145378768,
+    186056.26539522349504029498971604569928220784236328,
+    8071.6720023658162106380029022722506138218516325024,
+    210.82427775157934587250973392071336271166969580291,
+    2.5066282746310002701649081771338373386264310793408};
+__constant__ double c_lanczos_den[13] = {0.0,        39916800.0, 120543840.0, 150917976.0,
+                                         105258076.0, 45995730.0, 13339535.0,  2637558.0,
+                                         357423.0,    32670.0,    1925.0,      66.0,
+                                         1.0};
+
+__device__ double lgamma_cpython(double x) {
+    const double g = 6.024680040776729583740234375;
+    if (!(x > 0.0) || isinf(x)) return lgamma(x);   // outside the path's domain
+    if (x == floor(x) && x <= 2.0) return 0.0;
+    if (x < 1e-20) return -log(x);
+    double num = 0.0, den = 0.0;
+    if (x < 5.0) {
+        for (int i = 12; i >= 0; --i) {
+            num = __dadd_rn(__dmul_rn(num, x), c_lanczos_num[i]);
+            den = __dadd_rn(__dmul_rn(den, x), c_lanczos_den[i]);
+        }
+    } else {
+        for (int i = 0; i < 13; ++i) {
+            num = __dadd_rn(__ddiv_rn(num, x), c_lanczos_num[i]);
+            den = __dadd_rn(__ddiv_rn(den, x), c_lanczos_den[i]);
+        }
+    }
+    double r = __dsub_rn(log(__ddiv_rn(num, den)), g);
+    const double t = __dsub_rn(log(__dsub_rn(__dadd_rn(x, g), 0.5)), 1.0);
+    r = __dadd_rn(r, __dmul_rn(__dsub_rn(x, 0.5), t));
+    return r;
+}
+
+// matching_utils.py:21-25
+__device__ __forceinline__ double normpdf_dev(double x, double mean, double two_var,
+                                              double denom) {
+    const double dx = __dsub_rn(x, mean);
+    const double num = exp(__ddiv_rn(-__dmul_rn(dx, dx), two_var));
+    return __ddiv_rn(num, denom);
+}
+
+// matching_utils.py:36-39.  NaN when both Gaussians underflow (the reference raises
+// ZeroDivisionError there); the caller turns that into MCG_ERR_DOMAIN.
+__device__ __forceinline__ double comp_prob_dev(double d) {
+    const double gi = normpdf_dev(d, 0.0, c_gauss.two_var_intra, c_gauss.denom_intra);
+    const double ge = normpdf_dev(d, c_gauss.mu_inter, c_gauss.two_var_inter,
+                                  c_gauss.denom_inter);
+    return __ddiv_rn(gi, __dadd_rn(gi, ge));
+}
+
+// One sample of matching_utils.py:48-57: exp(c1*log(c2) - lgamma(c1+1) - c2), floored.
+__device__ __forceinline__ double poisson_term(double c1, double lg1, double c2, double logc2) {
+    double p = exp(__dsub_rn(__dsub_rn(__dmul_rn(c1, logc2), lg1), c2));
+    if (p < 1e-10) p = 1e-10;
+    return p;
+}
+
+// -(log(pc, 10) + log(pv, 10)) with math.log(x, 10) = log(x) / log(10)
+__device__ __forceinline__ double neg_log10_sum(double pc, double pv) {
+    return -__dadd_rn(__ddiv_rn(log(pc), c_gauss.ln10), __ddiv_rn(log(pv), c_gauss.ln10));
+}
+
+// ---- coverage terms --------------------------------------------------------------------
+__global__ void cov_terms_kernel(double *__restrict__ cov, double *__restrict__ logc,
+                                 double *__restrict__ lgam, long long count) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= count) return;
+    double c = cov[i];
+    if (c < 0.0001) c = 0.0001;   // feature_utils.py:152-153
+    cov[i] = c;
+    logc[i] = log(c);
+    lgam[i] = lgamma_cpython(__dadd_rn(c, 1.0));
+}
+
+// ---- tile staging ----------------------------------------------------------------------
+// dst[k][r ^ (k & 15)] = prof[row(r)][k]; rows past the end are zero.
+__device__ __forceinline__ void load_prof_tile(double *dst, const ScoreSide &s, long long r0) {
+    for (int idx = threadIdx.x; idx < kTile * MCG_NPROF; idx += kPairThreads) {
+        const int r = idx / MCG_NPROF;
+        const int k = idx - r * MCG_NPROF;
+        double v = 0.0;
+        if (r0 + r < s.n) {
+            const long long row = s.index ? s.index[r0 + r] : (r0 + r);
+            v = s.prof[row * MCG_NPROF + k];
+        }
+        dst[k * kTile + (r ^ (k & 15))] = v;
+    }
+}
+
+// dst[s][term][r] for samples [s0, s0+sc); rows past the end get c = 1 (log 0, lgamma 0).
+__device__ __forceinline__ void load_cov_chunk(double *dst, const ScoreSide &s, long long r0,
+                                               int S, int s0, int sc) {
+    for (int idx = threadIdx.x; idx < kTile * sc; idx += kPairThreads) {
+        const int r = idx / sc;
+        const int q = idx - r * sc;
+        double c = 1.0, lc = 0.0, lg = 0.0;
+        if (r0 + r < s.n) {
+            const long long row = s.index ? s.index[r0 + r] : (r0 + r);
+            const long long off = row * S + s0 + q;
+            c = s.cov[off];
+            lc = s.logc[off];
+            lg = s.lgam[off];
+        }
+        dst[(q * 3 + 0) * kTile + r] = c;
+        dst[(q * 3 + 1) * kTile + r] = lc;
+        dst[(q * 3 + 2) * kTile + r] = lg;
+    }
+}
+
+template <bool RULE_C>
+__global__ void __launch_bounds__(kPairThreads, 1)
+pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) double sm[];
+    double *As = sm;                              // [136][64]
+    double *Bs = As + MCG_NPROF * kTile;          // [136][64]
+    double *CA = Bs + MCG_NPROF * kTile;          // [16][3][64]
+    double *CB = CA + kSampleChunk * 3 * kTile;   // [16][3][64]
+
+    const int tid = threadIdx.x;
+    const int ti = tid >> 4, tj = tid & 15;
+    const long long a0 = static_cast<long long>(blockIdx.x) * kTile;
+    const long long n_btiles = (B.n + kTile - 1) / kTile;
+    const bool single_chunk = S <= kSampleChunk;
+
+    load_prof_tile(As, A, a0);
+    if (single_chunk) load_cov_chunk(CA, A, a0, S, 0, S);
+
+    double best_w[4];
+    int best_i[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { best_w[e] = 0.0; best_i[e] = -1; }
+    bool domain_error = false;
+
+    for (long long bt = blockIdx.y; bt < n_btiles; bt += gridDim.y) {
+        const long long b0 = bt * kTile;
+        __syncthreads();   // everyone is done with the previous Bs / CB
+        load_prof_tile(Bs, B, b0);
+        if (single_chunk) load_cov_chunk(CB, B, b0, S, 0, S);
+        __syncthreads();
+
+        // ---- squared tetramer distance (matching_utils.py:28-29) --------------------
+        double acc[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+#pragma unroll 2
+        for (int k = 0; k < MCG_NPROF; ++k) {
+            const int sw = k & 15;
+            const double *ar = As + k * kTile + (ti ^ sw);
+            const double *br = Bs + k * kTile + (tj ^ sw);
+            double a[4], b[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { a[e] = ar[16 * e]; b[e] = br[16 * e]; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const double d = a[e] - b[f];
+                    acc[e][f] = fma(d, d, acc[e][f]);
+                }
+        }
+
+        // ---- Poisson products over the samples, in sample order -----------------------
+        double p1[4][4], p2[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { p1[e][f] = 1.0; p2[e][f] = 1.0; }
+        for (int s0 = 0; s0 < S; s0 += kSampleChunk) {
+            const int sc = min(kSampleChunk, S - s0);
+            if (!single_chunk) {
+                __syncthreads();
+                load_cov_chunk(CA, A, a0, S, s0, sc);
+                load_cov_chunk(CB, B, b0, S, s0, sc);
+                __syncthreads();
+            }
+            for (int q = 0; q < sc; ++q) {
+                const double *ca = CA + q * 3 * kTile + ti;
+                const double *cb = CB + q * 3 * kTile + tj;
+                double ac[4], al[4], ag[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ac[e] = ca[16 * e];
+                    al[e] = ca[kTile + 16 * e];
+                    ag[e] = ca[2 * kTile + 16 * e];
+                }
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const double bc = cb[16 * f];
+                    const double bl = cb[kTile + 16 * f];
+                    const double bg = cb[2 * kTile + 16 * f];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // cov1 = the A row, cov2 = the B row (matching_utils.py:48-54)
+                        p1[e][f] = __dmul_rn(p1[e][f], poisson_term(ac[e], ag[e], bc, bl));
+                        p2[e][f] = __dmul_rn(p2[e][f], poisson_term(bc, bg, ac[e], al[e]));
+                    }
+                }
+            }
+        }
+
+        // ---- per-pair epilogue --------------------------------------------------------------
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long ar = a0 + ti + 16 * e;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const long long bc = b0 + tj + 16 * f;
+                if (ar >= A.n || bc >= B.n) continue;
+                const double dist = sqrt(acc[e][f]);
+                const double pc = comp_prob_dev(dist);
+                const double pv = p1[e][f] < p2[e][f] ? p1[e][f] : p2[e][f];
+                if (pc != pc) domain_error = true;
+                const bool valid = __dmul_rn(pc, pv) > 0.0;
+                const double lp = valid ? neg_log10_sum(pc, pv) : MCG_MAX_WEIGHT;
+                const long long o = ar * B.n + bc;
+                if (RULE_C) {
+                    // label_prop_utils.py:331-337: log_prob stays 0 unless the product is
+                    // positive, and an exact 0 becomes MAX_WEIGHT
+                    const double w = (valid && lp != 0.0) ? lp : MCG_MAX_WEIGHT;
+                    if (out.weights) out.weights[o] = w;
+                    const int bi = static_cast<int>(bc);
+                    if (best_i[e] < 0 || w < best_w[e] || (w == best_w[e] && bi < best_i[e])) {
+                        best_w[e] = w;
+                        best_i[e] = bi;
+                    }
+                } else {
+                    if (out.dist) out.dist[o] = dist;
+                    if (out.pc) out.pc[o] = pc;
+                    if (out.pv) out.pv[o] = pv;
+                    if (out.lp) out.lp[o] = lp;
+                }
+            }
+        }
+    }
+
+    if (domain_error) atomicOr(status, 1);
+
+    if (RULE_C) {
+        // first index of the minimum over the 16 column threads of each row
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            double w = best_w[e];
+            int bi = best_i[e];
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, w, m);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+                if (oi >= 0 && (bi < 0 || ow < w || (ow == w && oi < bi))) { w = ow; bi = oi; }
+            }
+            const long long ar = a0 + ti + 16 * e;
+            if (tj == 0 && ar < A.n) {
+                // label_prop_utils.py:342-345: None when the minimum is MAX_WEIGHT
+                const bool none = (bi < 0) || (w == MCG_MAX_WEIGHT);
+                if (out.argmin) out.argmin[ar] = none ? -1 : bi;
+                if (out.wmin) out.wmin[ar] = none ? MCG_MAX_WEIGHT : w;
+            }
+        }
+    }
+}
+
+// Rules A / B over a raw lp matrix [nq, nm]: members of bin b are the columns
+// seg_offsets[b] .. seg_offsets[b+1].  The sum runs in member order like the reference,
+// so MAX + finite = MAX and MAX + MAX = inf come out the same way.
+__global__ void aggregate_members_kernel(const double *__restrict__ lp, long long nq,
+                                         long long nm, const int64_t *__restrict__ seg_offsets,
+                                         long long nseg, int rule,
+                                         double *__restrict__ weights) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= nq * nseg) return;
+    const long long q = i / nseg, b = i - q * nseg;
+    const long long lo = seg_offsets[b], hi = seg_offsets[b + 1];
+    double sum = 0.0;
+    long long valid = 0;
+    for (long long j = lo; j < hi; ++j) {
+        const double v = lp[q * nm + j];
+        if (v != MCG_MAX_WEIGHT) ++valid;
+        sum = __dadd_rn(sum, v);
+    }
+    double w;
+    if (rule == MCG_RULE_A)
+        w = (sum != INFINITY) ? __ddiv_rn(sum, static_cast<double>(hi - lo)) : MCG_MAX_WEIGHT;
+    else
+        w = (sum != INFINITY && valid != 0) ? __ddiv_rn(sum, static_cast<double>(valid))
+                                            : MCG_MAX_WEIGHT;
+    weights[i] = w;
+}
+
+// feature_utils.py:232-233 np.mean(rows, axis=0): rows added in member order, one division.
+__global__ void segment_mean_kernel(const double *__restrict__ rows, int width,
+                                    const int64_t *__restrict__ members,
+                                    const int64_t *__restrict__ seg_offsets, long long nseg,
+                                    double *__restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= nseg * width) return;
+    const long long b = i / width;
+    const int k = static_cast<int>(i - b * width);
+    const long long lo = seg_offsets[b], hi = seg_offsets[b + 1];
+    double acc = 0.0;
+    for (long long j = lo; j < hi; ++j) {
+        const double v = rows[members[j] * width + k];
+        acc = (j == lo) ? v : __dadd_rn(acc, v);
+    }
+    out[i] = __ddiv_rn(acc, static_cast<double>(hi - lo));
+}
+
+// ---- elementwise primitives ----------------------------------------------------------------
+__global__ void normpdf_kernel(const double *__restrict__ x, double mean, double two_var,
+                               double denom, double *__restrict__ out, long long n) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = normpdf_dev(x[i], mean, two_var, denom);
+}
+
+__global__ void distance_kernel(const double *__restrict__ u, const double *__restrict__ v,
+                                long long n, int width, double *__restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int k = 0; k < width; ++k) {
+        const double d = u[i * width + k] - v[i * width + k];
+        acc = fma(d, d, acc);
+    }
+    out[i] = sqrt(acc);
+}
+
+__global__ void comp_prob_kernel(const double *__restrict__ dist, double *__restrict__ out,
+                                 long long n, int32_t *__restrict__ status) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const double p = comp_prob_dev(dist[i]);
+    if (p != p) atomicOr(status, 1);
+    out[i] = p;
+}
+
+// matching_utils.py:42-66 for one pair per thread (no hoisting: inputs are raw coverages).
+__global__ void cov_prob_kernel(const double *__restrict__ c1, const double *__restrict__ c2,
+                                long long n, int S, double *__restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    double p1 = 1.0, p2 = 1.0;
+    for (int s = 0; s < S; ++s) {
+        const double a = c1[i * S + s], b = c2[i * S + s];
+        p1 = __dmul_rn(p1, poisson_term(a, lgamma_cpython(__dadd_rn(a, 1.0)), b, log(b)));
+        p2 = __dmul_rn(p2, poisson_term(b, lgamma_cpython(__dadd_rn(b, 1.0)), a, log(a)));
+    }
+    out[i] = p1 < p2 ? p1 : p2;
+}
+
+// ---- FP64 FMA peak -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + i + threadIdx.x * 1e-3;
+    const double m = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 12345.678) out[0] = s;   // keeps the loop alive
+}
+
+}  // namespace
+
+// ---- launchers -------------------------------------------------------------------------------
+static int ensure_gauss(mcg_ctx *ctx) {
+    static bool ready[64] = {};
+    if (ctx->device < 64 && ready[ctx->device]) return MCG_OK;
+    GaussConst g;
+    const double sd_i = 0.01037897 / 2, sd_e = 0.03419337;
+    const double root = sqrt(2 * 3.141592653589793);   // (2 * math.pi) ** 0.5
+    g.two_var_intra = 2 * (sd_i * sd_i);
+    g.denom_intra = sd_i * root;
+    g.mu_inter = 0.0676654;
+    g.two_var_inter = 2 * (sd_e * sd_e);
+    g.denom_inter = sd_e * root;
+    g.ln10 = log(10.0);
+    MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss, &g, sizeof g, 0, cudaMemcpyHostToDevice,
+                                          ctx->stream));
+    MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kPairSmem)));
+    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kPairSmem)));
+    if (ctx->device < 64) ready[ctx->device] = true;
+    return MCG_OK;
+}
+
+static inline unsigned blocks_for(long long n, int threads) {
+    return static_cast<unsigned>((n + threads - 1) / threads);
+}
+
+int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam, int64_t count) {
+    if (count == 0) return MCG_OK;
+    cov_terms_kernel<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(d_cov, d_logc, d_lgam,
+                                                                      count);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samples,
+                const ScoreOut &out, int32_t *d_status) {
+    MCG_TRY(ensure_gauss(ctx));
+    if (a.n == 0) return MCG_OK;
+    const bool rule_c = out.argmin != nullptr || out.wmin != nullptr || out.weights != nullptr;
+    const long long a_tiles = (a.n + kTile - 1) / kTile;
+    const long long b_tiles = (b.n + kTile - 1) / kTile;
+    if (a_tiles > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many query rows");
+    dim3 grid(static_cast<unsigned>(a_tiles), 1, 1);
+    if (rule_c) {
+        pair_kernel<true><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(a, b, n_samples, out,
+                                                                          d_status);
+    } else {
+        // few query tiles: spread the B tiles over grid.y to fill the SMs
+        long long gy = (2LL * ctx->sm_count + a_tiles - 1) / a_tiles;
+        if (gy > b_tiles) gy = b_tiles;
+        if (gy < 1) gy = 1;
+        if (gy > 65535) gy = 65535;
+        grid.y = static_cast<unsigned>(gy);
+        pair_kernel<false><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(a, b, n_samples, out,
+                                                                           d_status);
+    }
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_aggregate_members(mcg_ctx *ctx, const double *d_lp, int64_t nq, int64_t nm,
+                            const int64_t *d_seg_offsets, int64_t nseg, int rule,
+                            double *d_weights) {
+    if (nq * nseg == 0) return MCG_OK;
+    aggregate_members_kernel<<<blocks_for(nq * nseg, 128), 128, 0, ctx->stream>>>(
+        d_lp, nq, nm, d_seg_offsets, nseg, rule, d_weights);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_segment_mean(mcg_ctx *ctx, const double *d_rows, int width, const int64_t *d_members,
+                       const int64_t *d_seg_offsets, int64_t nseg, double *d_out) {
+    if (nseg * width == 0) return MCG_OK;
+    segment_mean_kernel<<<blocks_for(nseg * width, 128), 128, 0, ctx->stream>>>(
+        d_rows, width, d_members, d_seg_offsets, nseg, d_out);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_normpdf(mcg_ctx *ctx, const double *d_x, double mean, double sd, double *d_out,
+                  int64_t n) {
+    if (n == 0) return MCG_OK;
+    const double two_var = 2 * (sd * sd);
+    const double denom = sd * sqrt(2 * 3.141592653589793);
+    normpdf_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_x, mean, two_var, denom, d_out,
+                                                                n);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_distance(mcg_ctx *ctx, const double *d_u, const double *d_v, int64_t n, int width,
+                   double *d_out) {
+    if (n == 0) return MCG_OK;
+    distance_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(d_u, d_v, n, width, d_out);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_comp_prob(mcg_ctx *ctx, const double *d_dist, double *d_out, int64_t n,
+                    int32_t *d_status) {
+    MCG_TRY(ensure_gauss(ctx));
+    if (n == 0) return MCG_OK;
+    comp_prob_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_dist, d_out, n, d_status);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_cov_prob(mcg_ctx *ctx, const double *d_c1, const double *d_c2, int64_t n, int S,
+                   double *d_out) {
+    if (n == 0) return MCG_OK;
+    cov_prob_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(d_c1, d_c2, n, S, d_out);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_fp64_peak(mcg_ctx *ctx, double *tflops) {
+    const int iters = 4096;
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[5], 64));
+    cudaEvent_t e0, e1;
+    MCG_CUDA(ctx, cudaEventCreate(&e0));
+    MCG_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        MCG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->scratch[5].as<double>(), iters,
+                                                              1.0 + rep);
+        MCG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        MCG_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        MCG_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 64.0 * iters * static_cast<double>(blocks) * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return MCG_OK;
+}
