@@ -1,0 +1,404 @@
+#!/usr/bin/env python3
+"""Headline benchmark: contigs/s for featurise + score (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): synthetic metaSPAdes-style contig set, 100 000 contigs
+of 1-50 kb (log-uniform, ~1.28 Gbp), 10 coverage samples, 200 marker-seeded bins, per GPU.
+One step = one pass of the hot path over that set: tetramer scan of the 2-bit store ->
+normalise -> coverage terms -> rule-C scoring of every contig against every bin centroid
+(label_prop_utils.assign_long) -> argmin.  At N > 1 every rank owns its own 100k-contig
+shard (weak scaling), rank 0's centroids are broadcast and the assignments all-gathered
+with NCCL inside the step.
+
+`value`   inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     the same work through mcg_featurise_score from pinned HOST buffers (ASCII bases,
+          coverages, centroids in; assignments out), copies inside the timed region.
+`roofline`/`kernels`  per-kernel device times from CUDA events on the launching stream.
+`cpu_baseline`        the CPU oracle (C port of the reference arithmetic) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_CONTIGS = int(os.environ.get("MCG_BENCH_CONTIGS", 100000))
+N_SAMPLES = int(os.environ.get("MCG_BENCH_SAMPLES", 10))
+N_BINS = int(os.environ.get("MCG_BENCH_BINS", 200))
+WORKLOAD = "synthetic metaSPAdes-style %dk contigs (1-50 kb), %d samples, %d bins per GPU" % (
+    N_CONTIGS // 1000, N_SAMPLES, N_BINS)
+METRIC = "contigs/sec featurise+score"
+
+
+def workload_tables(seed, n_contigs, n_samples, n_bins):
+    """Everything of the synthetic data set except the bases."""
+    from metacoag_b200 import synth
+    rng = np.random.default_rng(seed)
+    dinuc, abundance = synth.genome_tables(rng, n_bins, n_samples)
+    trans = dinuc.reshape(n_bins, 4, 4)
+    trans = (trans / trans.sum(axis=2, keepdims=True)).astype(np.float32)
+    lengths = synth.sample_lengths(rng, n_contigs, "spades")
+    genome_of = rng.integers(0, n_bins, n_contigs).astype(np.int32)
+    offsets = np.zeros(n_contigs + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    noise = np.clip(rng.normal(1.0, 0.1, (n_contigs, n_samples)), 0.0, None)
+    raw = abundance[genome_of] * noise
+    raw[rng.random((n_contigs, n_samples)) < 0.01] = 0.0
+    coverage = np.round(raw, 4)            # the "%.4f" of the abundance file
+    coverage[coverage < 1e-4] = 1e-4       # feature_utils.py:152-153
+    # marker-seeded bins: up to 20 contigs >= 3 kb of every genome
+    members, seg = [], [0]
+    order = np.argsort(genome_of, kind="stable")
+    starts = np.searchsorted(genome_of[order], np.arange(n_bins + 1))
+    for g in range(n_bins):
+        ids = order[starts[g]:starts[g + 1]]
+        ids = ids[lengths[ids] >= 3000][:20]
+        if ids.size == 0:
+            ids = order[starts[g]:starts[g] + 1] if starts[g + 1] > starts[g] else np.array([g])
+        members.extend(int(i) for i in ids)
+        seg.append(len(members))
+    return dict(trans=trans, lengths=lengths, genome_of=genome_of, offsets=offsets,
+                coverage=np.ascontiguousarray(coverage), members=np.array(members, np.int64),
+                seg=np.array(seg, np.int64))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "50", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_pass(oracle, blob, offsets, coverage, cen_prof, cen_cov, lo, hi, nthreads):
+    """The reference arithmetic for contigs lo:hi on the host cores (C port, pthreads)."""
+    sub_off = offsets[lo:hi + 1] - offsets[lo]
+    sub_blob = blob[int(offsets[lo]):int(offsets[hi])]
+    _, freqs = oracle.count_kmers_batch(sub_blob, sub_off, want_counts=False, nthreads=nthreads)
+    cov = coverage[lo:hi].copy()
+    cov[cov < 1e-4] = 1e-4
+    arg, w, _ = oracle.score_centroids(freqs, cov, cen_prof, cen_cov, nthreads=nthreads)
+    return arg, w
+
+
+def cpu_baseline(blob, offsets, coverage, cen_prof, cen_cov, budget_s):
+    from oracle import oracle
+    cores = oracle.max_threads()
+    n = offsets.shape[0] - 1
+    probe = min(n, 256)
+    t0 = time.perf_counter()
+    oracle_pass(oracle, blob, offsets, coverage, cen_prof, cen_cov, 0, probe, 0)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(n, max(probe, rate * budget_s)))
+    t0 = time.perf_counter()
+    oracle_pass(oracle, blob, offsets, coverage, cen_prof, cen_cov, 0, sample, 0)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "contigs/s", "cores": cores, "kind": "port",
+            "sample": "first %d contigs (%.1f Mbp) x %d bins, %d samples, %.1f s" % (
+                sample, (offsets[sample] - offsets[0]) / 1e6, cen_prof.shape[0],
+                coverage.shape[1], dt)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU arithmetic (oracle port; the reference itself is
+    pure Python and cannot travel) on the same workload, bounded sample per step."""
+    if rank != 0:
+        return
+    from metacoag_b200 import _lib
+    from oracle import oracle
+    tabs = workload_tables(1001, N_CONTIGS, N_SAMPLES, N_BINS)
+    # the bases come from the same device generator as the CUDA arm (setup, not timed)
+    ctx = _lib.Context(0)
+    blob = ctx.synth_bases(tabs["offsets"], tabs["genome_of"], tabs["trans"], 1001)
+    ctx.close()
+    cores = oracle.max_threads()
+    offsets, coverage = tabs["offsets"], tabs["coverage"]
+    # bin centroids from the seed members, on the CPU as well (feature_utils.py:217-235)
+    mem = tabs["members"]
+    mem_off = np.zeros(mem.shape[0] + 1, dtype=np.int64)
+    np.cumsum(tabs["lengths"][mem], out=mem_off[1:])
+    mem_blob = np.concatenate([blob[offsets[i]:offsets[i + 1]] for i in mem])
+    _, mem_prof = oracle.count_kmers_batch(mem_blob, mem_off, want_counts=False, nthreads=0)
+    local_ids = np.arange(mem.shape[0], dtype=np.int64)
+    cen_prof = oracle.segment_mean(mem_prof, local_ids, tabs["seg"])
+    cen_cov = oracle.segment_mean(coverage[mem], local_ids, tabs["seg"])
+    probe = 256
+    t0 = time.perf_counter()
+    oracle_pass(oracle, blob, offsets, coverage, cen_prof, cen_cov, 0, probe, 0)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    per_step_s = 120.0 / max(1, args.steps + args.warmup)
+    sample = int(min(N_CONTIGS, max(probe, rate * per_step_s)))
+    for _ in range(args.warmup):
+        oracle_pass(oracle, blob, offsets, coverage, cen_prof, cen_cov, 0, sample, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_pass(oracle, blob, offsets, coverage, cen_prof, cen_cov, 0, sample, 0)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    desc = "first %d contigs (%.1f Mbp) x %d bins per step, %d host threads" % (
+        sample, offsets[sample] / 1e6, N_BINS, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "contigs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "contigs/s", "cores": cores, "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": value, "unit": "contigs/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from metacoag_b200 import _lib, parallel
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- setup (untimed) ---------------------------------------------------------------
+    seed = 1001 + rank
+    tabs = workload_tables(seed, N_CONTIGS, N_SAMPLES, N_BINS)
+    offsets, coverage = tabs["offsets"], tabs["coverage"]
+    n, n_bases = N_CONTIGS, int(offsets[-1])
+    ctx = _lib.Context(local)
+    # a non-default torch stream: the library, the NCCL collectives and the timing events
+    # all run on it (handle 0 would mean "the context's own stream" to mcg_set_stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+
+    blob = _lib.pinned_empty(n_bases)
+    ctx.synth_bases(offsets, tabs["genome_of"], tabs["trans"], seed, out=blob)
+    pin_cov = _lib.pinned_empty(coverage.nbytes).view(np.float64).reshape(coverage.shape)
+    pin_cov[:] = coverage
+    pin_off = _lib.pinned_empty(offsets.nbytes).view(np.int64)
+    pin_off[:] = offsets
+
+    ctx.load_contigs(blob, pin_off)
+    ctx.load_coverage(pin_cov)
+    ctx.scan()
+    cen_prof, cen_cov = ctx.bin_profiles(tabs["members"], tabs["seg"])
+    d_cen_prof = torch.from_numpy(cen_prof).to(dev)
+    d_cen_cov = torch.from_numpy(cen_cov).to(dev)
+    d_argmin = torch.empty(n, dtype=torch.int32, device=dev)
+    d_wmin = torch.empty(n, dtype=torch.float64, device=dev)
+    fp64_peak = ctx.fp64_peak()
+
+    def step():
+        if world > 1:
+            parallel.broadcast_centroids(d_cen_prof, d_cen_cov, src=0)
+            ctx.set_centroids_dev(d_cen_prof.data_ptr(), d_cen_cov.data_ptr(), N_BINS)
+        ctx.step_resident(d_argmin.data_ptr(), d_wmin.data_ptr())
+        if world > 1:
+            return parallel.gather_assignments(d_argmin, d_wmin, counts=[n] * world)
+        return d_argmin, d_wmin
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- per-kernel device times (CUDA events on the launching stream) ------------------
+    ctx.profile(True)
+    kernel_ms = {}
+    reps = 5
+    launches_per_step = 0
+    for _ in range(reps):
+        step()
+        t = ctx.timings()
+        launches_per_step = t.pop("launches")
+        for k, v in t.items():
+            kernel_ms[k] = kernel_ms.get(k, 0.0) + v / reps
+    ctx.profile(False)
+    barrier()
+
+    # ---- timed region ------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the plug-in call, host buffers --------------------------------------
+    h_arg = _lib.pinned_empty(4 * n).view(np.int32)
+    h_w = _lib.pinned_empty(8 * n).view(np.float64)
+    ctx.featurise_score(blob, pin_off, pin_cov, cen_prof, cen_cov, argmin=h_arg, wmin=h_w)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.featurise_score(blob, pin_off, pin_cov, cen_prof, cen_cov, argmin=h_arg, wmin=h_w)
+        if world > 1:
+            parallel.gather_assignments(torch.from_numpy(h_arg).to(dev, non_blocking=True),
+                                        torch.from_numpy(h_w).to(dev, non_blocking=True),
+                                        counts=[n] * world)
+            torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e2e.item())
+    ctx.profile(True)
+    ctx.featurise_score(blob, pin_off, pin_cov, cen_prof, cen_cov, argmin=h_arg, wmin=h_w)
+    e2e_ms = ctx.timings()
+    e2e_ms.pop("launches")
+    ctx.profile(False)
+    h2d = n_bases + offsets.nbytes + 16 * n + coverage.nbytes + cen_prof.nbytes + cen_cov.nbytes
+    d2h = 12 * n + 16
+
+    # device results of the last resident step agree with the plug-in call
+    ctx.step_resident(d_argmin.data_ptr(), d_wmin.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_argmin.cpu().numpy(), h_arg)
+
+    # ---- roofline -----------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650"
+    lens = tabs["lengths"]
+    n_seg = int(np.sum((np.maximum(lens - 3, 0) + 255) // 256))
+    scan_bytes = float(np.sum((lens + 3) // 4) + n * 136 * 4 + 4 * n_seg)
+    pairs = float(n) * N_BINS
+    score_flops = pairs * (431 + 14 * N_SAMPLES)
+    scan_roof = {"kernel": "scan_kernel", "bound": "hbm",
+                 "achieved": scan_bytes / (kernel_ms["scan"] * 1e-3) / 1e9, "peak": hbm_peak,
+                 "unit": "GB/s", "peak_source": hbm_src, "traffic": None,
+                 "algorithmic_bytes": scan_bytes, "ms": kernel_ms["scan"],
+                 "gbases_per_s": n_bases / (kernel_ms["scan"] * 1e-3) / 1e9}
+    scan_roof["frac"] = scan_roof["achieved"] / scan_roof["peak"]
+    score_roof = {"kernel": "pair_kernel<rule C>", "bound": "fp64",
+                  "achieved": score_flops / (kernel_ms["score"] * 1e-3) / 1e12,
+                  "peak": fp64_peak, "unit": "TFLOP/s",
+                  "peak_source": "DFMA microbenchmark on this device (mcg_fp64_peak)",
+                  "traffic": None, "algorithmic_flops": score_flops, "ms": kernel_ms["score"],
+                  "gpairs_per_s": pairs / (kernel_ms["score"] * 1e-3) / 1e9}
+    score_roof["frac"] = score_roof["achieved"] / score_roof["peak"]
+    dominant = score_roof if kernel_ms["score"] >= kernel_ms["scan"] else scan_roof
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "contigs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "contigs_per_gpu": n, "bases_per_gpu": n_bases,
+                   "samples": N_SAMPLES, "bins": N_BINS,
+                   "parallelism": "row-sharded x%d, NCCL broadcast + all-gather" % world,
+                   "l2": "inputs larger than L2 (%.0f MB packed bases + %.0f MB profiles per step)"
+                         % (n_bases / 4e6, n * 136 * 8 / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": n * world / e2e_s, "unit": "contigs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
+                "steps": args.e2e_steps, "device_ms": e2e_ms},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": dominant,
+        "roofline_kernels": [scan_roof, score_roof],
+        "kernel_ms": kernel_ms,
+    }
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_baseline(blob, offsets, coverage, cen_prof, cen_cov,
+                                            args.cpu_budget)
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

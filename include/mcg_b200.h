@@ -165,6 +165,10 @@ int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
  * DEVICE pointers, or NULL to use context-owned buffers). */
 int mcg_set_centroids(mcg_ctx *ctx, const double *cen_prof, const double *cen_cov,
                       int64_t n_bins);
+/* Same, from DEVICE buffers (e.g. the tensors an NCCL broadcast just filled);
+ * stream-ordered on the context's stream, no host synchronisation. */
+int mcg_set_centroids_dev(mcg_ctx *ctx, const void *d_cen_prof, const void *d_cen_cov,
+                          int64_t n_bins);
 int mcg_step_resident(mcg_ctx *ctx, void *d_argmin, void *d_wmin);
 int mcg_get_assignments(mcg_ctx *ctx, int32_t *argmin, double *wmin);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mcg_featurise_score": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _i64, _vp,
                                    _vp]),
     "mcg_set_centroids": (_int, [_vp, _vp, _vp, _i64]),
+    "mcg_set_centroids_dev": (_int, [_vp, _vp, _vp, _i64]),
     "mcg_step_resident": (_int, [_vp, _vp, _vp]),
     "mcg_get_assignments": (_int, [_vp, _vp, _vp]),
     "mcg_profile": (_int, [_vp, _int]),
@@ -352,6 +353,12 @@ class Context:
         self._check(self.lib.mcg_set_centroids(self.handle, _ptr(cen_prof), _ptr(cen_cov),
                                                cen_prof.shape[0]))
         self.n_bins = cen_prof.shape[0]
+
+    def set_centroids_dev(self, d_cen_prof, d_cen_cov, n_bins):
+        """Centroids from device pointers (ints), stream-ordered, no host sync."""
+        self._check(self.lib.mcg_set_centroids_dev(self.handle, d_cen_prof, d_cen_cov,
+                                                   int(n_bins)))
+        self.n_bins = int(n_bins)
 
     def step_resident(self, d_argmin=None, d_wmin=None):
         self._check(self.lib.mcg_step_resident(self.handle, d_argmin, d_wmin))

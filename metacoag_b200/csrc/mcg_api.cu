@@ -456,6 +456,27 @@ extern "C" int mcg_set_centroids(mcg_ctx *ctx, const double *cen_prof, const dou
     return sync(ctx);
 }
 
+extern "C" int mcg_set_centroids_dev(mcg_ctx *ctx, const void *d_cen_prof, const void *d_cen_cov,
+                                     int64_t B) {
+    MCG_ENTER(ctx);
+    const int S = ctx->n_samples;
+    if (S <= 0) return mcg_fail(ctx, MCG_ERR_STATE, "load coverage before centroids");
+    if (B <= 0 || !d_cen_prof || !d_cen_cov) return mcg_fail(ctx, MCG_ERR_ARG, "bad centroid arguments");
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_prof, sizeof(double) * MCG_NPROF * B));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_cov, sizeof(double) * S * B));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_logc, sizeof(double) * S * B));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_lgam, sizeof(double) * S * B));
+    MCG_CUDA(ctx, cudaMemcpyAsync(ctx->cen_prof.p, d_cen_prof, sizeof(double) * MCG_NPROF * B,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    MCG_CUDA(ctx, cudaMemcpyAsync(ctx->cen_cov.p, d_cen_cov, sizeof(double) * S * B,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    MCG_TRY(mcg_k_cov_terms(ctx, ctx->cen_cov.as<double>(), ctx->cen_logc.as<double>(),
+                            ctx->cen_lgam.as<double>(), B * S));
+    ctx->n_bins = B;
+    ctx->cen_samples = S;
+    return MCG_OK;
+}
+
 extern "C" int mcg_bin_profiles(mcg_ctx *ctx, const int64_t *members, const int64_t *seg_offsets,
                                 int64_t nseg, double *cen_prof, double *cen_cov) {
     MCG_ENTER(ctx);

@@ -73,14 +73,14 @@ __device__ __forceinline__ uint4 ldg_u4(const uint32_t *p) {
 template <int I>
 __device__ __forceinline__ uint32_t window_addr(uint32_t lo, uint32_t hi, uint32_t lanebase) {
     uint32_t y, z;
-    if (2 * I >= 5)
-        y = __funnelshift_r(lo, hi, 2 * I - 5);
+    if constexpr (2 * I >= 5)
+        y = __funnelshift_r(lo, hi, static_cast<uint32_t>(2 * I - 5));
     else
-        y = lo << (5 - 2 * I);
-    if (I == 0)
+        y = lo << static_cast<uint32_t>(5 - 2 * I);
+    if constexpr (I == 0)
         z = lo;
     else
-        z = __funnelshift_r(lo, hi, 2 * I);
+        z = __funnelshift_r(lo, hi, static_cast<uint32_t>(2 * I));
     return and_or(z, 3u, and_or(y, 0x1F80u, lanebase));
 }
 
