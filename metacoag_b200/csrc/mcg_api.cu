@@ -161,7 +161,7 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->packed, &ctx->meta, &ctx->seg_contig, &ctx->ascii, &ctx->offsets,
                       &ctx->tile_counter, &ctx->counts, &ctx->prof, &ctx->cov, &ctx->logc,
                       &ctx->lgam, &ctx->cen_prof, &ctx->cen_cov, &ctx->cen_logc, &ctx->cen_lgam,
-                      &ctx->argmin, &ctx->wmin, &ctx->status};
+                      &ctx->argmin, &ctx->wmin, &ctx->status, &ctx->prof_norm, &ctx->cen_norm};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->scratch)
@@ -316,6 +316,8 @@ static int scan_locked(mcg_ctx *ctx) {
         MCG_TRY(mcg_k_normalise(ctx, ctx->counts.as<uint32_t>(), ctx->meta.as<ContigMeta>(), n,
                                 ctx->prof.as<double>()));
     }
+    MCG_TRY(mcg_reserve(ctx, ctx->prof_norm, sizeof(double) * std::max<int64_t>(n, 1)));
+    MCG_TRY(mcg_k_row_norms(ctx, ctx->prof.as<double>(), n, ctx->prof_norm.as<double>()));
     ctx->n_prof = n;
     return MCG_OK;
 }
@@ -368,6 +370,8 @@ extern "C" int mcg_set_profiles(mcg_ctx *ctx, const double *prof, int64_t n) {
     if (n < 0 || (n > 0 && !prof)) return mcg_fail(ctx, MCG_ERR_ARG, "bad profile arguments");
     MCG_TRY(mcg_reserve(ctx, ctx->prof, sizeof(double) * MCG_NPROF * std::max<int64_t>(n, 1)));
     MCG_TRY(h2d(ctx, ctx->prof.p, prof, sizeof(double) * MCG_NPROF * n));
+    MCG_TRY(mcg_reserve(ctx, ctx->prof_norm, sizeof(double) * std::max<int64_t>(n, 1)));
+    MCG_TRY(mcg_k_row_norms(ctx, ctx->prof.as<double>(), n, ctx->prof_norm.as<double>()));
     MCG_TRY(sync(ctx));
     ctx->n_prof = n;
     return MCG_OK;
@@ -443,6 +447,8 @@ static int set_centroids_locked(mcg_ctx *ctx, const double *cen_prof, const doub
     // centroid coverages are means of clamped values, so the clamp in the kernel is inert
     MCG_TRY(mcg_k_cov_terms(ctx, ctx->cen_cov.as<double>(), ctx->cen_logc.as<double>(),
                             ctx->cen_lgam.as<double>(), B * S));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_norm, sizeof(double) * B));
+    MCG_TRY(mcg_k_row_norms(ctx, ctx->cen_prof.as<double>(), B, ctx->cen_norm.as<double>()));
     ctx->n_bins = B;
     ctx->cen_samples = S;
     return MCG_OK;
@@ -472,6 +478,8 @@ extern "C" int mcg_set_centroids_dev(mcg_ctx *ctx, const void *d_cen_prof, const
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     MCG_TRY(mcg_k_cov_terms(ctx, ctx->cen_cov.as<double>(), ctx->cen_logc.as<double>(),
                             ctx->cen_lgam.as<double>(), B * S));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_norm, sizeof(double) * B));
+    MCG_TRY(mcg_k_row_norms(ctx, ctx->cen_prof.as<double>(), B, ctx->cen_norm.as<double>()));
     ctx->n_bins = B;
     ctx->cen_samples = S;
     return MCG_OK;
@@ -506,6 +514,8 @@ extern "C" int mcg_bin_profiles(mcg_ctx *ctx, const int64_t *members, const int6
     if (cen_cov) MCG_TRY(d2h(ctx, cen_cov, ctx->cen_cov.p, sizeof(double) * S * nseg));
     MCG_TRY(mcg_k_cov_terms(ctx, ctx->cen_cov.as<double>(), ctx->cen_logc.as<double>(),
                             ctx->cen_lgam.as<double>(), nseg * S));
+    MCG_TRY(mcg_reserve(ctx, ctx->cen_norm, sizeof(double) * nseg));
+    MCG_TRY(mcg_k_row_norms(ctx, ctx->cen_prof.as<double>(), nseg, ctx->cen_norm.as<double>()));
     ctx->n_bins = nseg;
     ctx->cen_samples = S;
     return sync(ctx);
@@ -578,6 +588,7 @@ static ScoreSide contig_side(mcg_ctx *ctx, const int64_t *d_index, int64_t n) {
     s.cov = ctx->cov.as<double>();
     s.logc = ctx->logc.as<double>();
     s.lgam = ctx->lgam.as<double>();
+    s.norm = ctx->prof_norm.as<double>();
     s.index = d_index;
     s.n = n;
     return s;
@@ -589,6 +600,7 @@ static ScoreSide centroid_side(mcg_ctx *ctx) {
     s.cov = ctx->cen_cov.as<double>();
     s.logc = ctx->cen_logc.as<double>();
     s.lgam = ctx->cen_lgam.as<double>();
+    s.norm = ctx->cen_norm.as<double>();
     s.index = nullptr;
     s.n = ctx->n_bins;
     return s;

@@ -56,6 +56,7 @@ struct mcg_ctx {
     int64_t n_prof = 0;
     DevBuf counts;             // uint32 [n_prof,136]
     DevBuf prof;               // f64 [n_prof,136]
+    DevBuf prof_norm;          // f64 [n_prof] squared row norms
     int64_t n_cov = 0;
     int n_samples = 0;
     DevBuf cov, logc, lgam;    // f64 [n_cov,S] each
@@ -64,6 +65,7 @@ struct mcg_ctx {
     int64_t n_bins = 0;
     int cen_samples = 0;
     DevBuf cen_prof;           // f64 [B,136]
+    DevBuf cen_norm;           // f64 [B]
     DevBuf cen_cov, cen_logc, cen_lgam;   // f64 [B,S]
 
     // ---- results / scratch ---------------------------------------------------------
@@ -144,6 +146,7 @@ struct ScoreSide {
     const double *cov;    // [rows,S]
     const double *logc;   // [rows,S]
     const double *lgam;   // [rows,S]
+    const double *norm;   // [rows] squared L2 norm of each profile row
     const int64_t *index; // gather index or nullptr (identity)
     int64_t n;            // rows addressed on this side
 };
@@ -156,6 +159,7 @@ struct ScoreOut {
     double *dist = nullptr, *pc = nullptr, *pv = nullptr, *lp = nullptr;  // [na,nb]
 };
 int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam, int64_t count);
+int mcg_k_row_norms(mcg_ctx *ctx, const double *d_prof, int64_t rows, double *d_norm);
 int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samples,
                 const ScoreOut &out, int32_t *d_status);
 int mcg_k_aggregate_members(mcg_ctx *ctx, const double *d_lp, int64_t nq, int64_t nm,

@@ -226,29 +226,37 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
         __syncwarp();
 
         // ---- flush: lane j sums table rows j and j+32 over the 32 columns ---------
-        uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-        int run = contig;   // first column visited is the lane's own
+        // Columns of one contig are adjacent lanes; the runs are warp-uniform, so all lanes
+        // walk the same run at the same time and emit together.  Inside a run lane j starts
+        // at column c0 + j mod len, which keeps bank = column distinct across lanes when
+        // the run spans the warp (the common case).
         const uint32_t rowA = tab + lane * 128u;
+        const int prev = __shfl_up_sync(0xffffffffu, contig, 1);
+        uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || contig != prev);
+        while (heads) {
+            const int c0 = __ffs(heads) - 1;
+            heads &= heads - 1;
+            const int c1 = heads ? (__ffs(heads) - 1) : 32;
+            const int len = c1 - c0;
+            const int run_contig = __shfl_sync(0xffffffffu, contig, c0);
+            if (run_contig < 0) continue;   // idle lanes: their columns were never touched
+            uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            int col = c0 + static_cast<int>(lane) % len;
 #pragma unroll 4
-        for (int t = 0; t < 32; ++t) {
-            const uint32_t col = (lane + t) & 31u;
-            const int cc = __shfl_sync(0xffffffffu, contig, col);
-            if (cc != run) {
-                emit_run(counts, run, a0, a1, b0, b1, canA, canB);
-                a0 = a1 = b0 = b1 = 0;
-                run = cc;
+            for (int t = 0; t < len; ++t) {
+                const uint32_t addrA = rowA + col * 4u;
+                const uint32_t wA = lds_u32(addrA);
+                const uint32_t wB = lds_u32(addrA + 4096u);
+                sts_u32(addrA, 0u);
+                sts_u32(addrA + 4096u, 0u);
+                a0 += wA & 0x00FF00FFu;
+                a1 += (wA >> 8) & 0x00FF00FFu;
+                b0 += wB & 0x00FF00FFu;
+                b1 += (wB >> 8) & 0x00FF00FFu;
+                if (++col == c1) col = c0;
             }
-            const uint32_t addrA = rowA + col * 4u;
-            const uint32_t wA = lds_u32(addrA);
-            const uint32_t wB = lds_u32(addrA + 4096u);
-            sts_u32(addrA, 0u);
-            sts_u32(addrA + 4096u, 0u);
-            a0 += wA & 0x00FF00FFu;
-            a1 += (wA >> 8) & 0x00FF00FFu;
-            b0 += wB & 0x00FF00FFu;
-            b1 += (wB >> 8) & 0x00FF00FFu;
+            emit_run(counts, run_contig, a0, a1, b0, b1, canA, canB);
         }
-        emit_run(counts, run, a0, a1, b0, b1, canA, canB);
         __syncwarp();
     }
 }

@@ -24,9 +24,7 @@ namespace {
 
 constexpr int kTile = 64;          // rows per side per CTA tile
 constexpr int kPairThreads = 256;
-constexpr int kSampleChunk = 16;   // samples staged per pass
-constexpr size_t kPairSmem =
-    sizeof(double) * (2 * MCG_NPROF * kTile + 2 * kSampleChunk * 3 * kTile);
+constexpr int kSampleChunk = 12;   // samples staged per pass
 
 // matching_utils.py:12-15
 struct GaussConst {
@@ -98,9 +96,38 @@ __device__ __forceinline__ double comp_prob_dev(double d) {
     return __ddiv_rn(gi, __dadd_rn(gi, ge));
 }
 
+// ---- exp for the Poisson terms -------------------------------------------------------------
+// exp(x) = 2^(k/16) * e^r with k = round(16 x / ln 2), |r| <= ln2/32: a 16-entry table of
+// 2^(j/16) (one 128-byte shared-memory wavefront, so 32 lanes with 32 different arguments
+// never conflict) times a degree-7 Taylor polynomial (truncation 1.2e-18), exponent added
+// as an integer.  ~12 FP64 instructions against ~28 for the library exp(); < 2 ulp.
+// Arguments below -100 are clamped: the callers floor the result at 1e-10 anyway
+// (matching_utils.py:56-60), and the clamp keeps the exponent arithmetic in the normal range.
+__device__ double g_exp_table[16];
+
+__device__ __forceinline__ double exp_tab16(double x, const double *__restrict__ table) {
+    const double xc = x < -100.0 ? -100.0 : x;
+    const double kd = fma(xc, 23.083120654223414, 6755399441055744.0);   // 16/ln2, 1.5*2^52
+    const int ki = __double2loint(kd);
+    const double kf = kd - 6755399441055744.0;
+    double r = fma(kf, -0x1.62e42ff000000p-5, xc);    // ln2/16, high 32 bits
+    r = fma(kf, 0x1.718432a1b0e26p-39, r);            // minus the low part
+    double q = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+    q = fma(q, r, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    const double em1 = fma(q, r * r, r);
+    const double t = table[ki & 15];
+    const double res = fma(t, em1, t);
+    const int hi = __double2hiint(res) + ((ki >> 4) << 20);
+    return __hiloint2double(hi, __double2loint(res));
+}
+
 // One sample of matching_utils.py:48-57: exp(c1*log(c2) - lgamma(c1+1) - c2), floored.
-__device__ __forceinline__ double poisson_term(double c1, double lg1, double c2, double logc2) {
-    double p = exp(__dsub_rn(__dsub_rn(__dmul_rn(c1, logc2), lg1), c2));
+__device__ __forceinline__ double poisson_term(double c1, double lg1, double c2, double logc2,
+                                               const double *__restrict__ table) {
+    double p = exp_tab16(__dsub_rn(__dsub_rn(__dmul_rn(c1, logc2), lg1), c2), table);
     if (p < 1e-10) p = 1e-10;
     return p;
 }
@@ -122,30 +149,51 @@ __global__ void cov_terms_kernel(double *__restrict__ cov, double *__restrict__ 
     lgam[i] = lgamma_cpython(__dadd_rn(c, 1.0));
 }
 
-// ---- tile staging ----------------------------------------------------------------------
-// dst[k][r ^ (k & 15)] = prof[row(r)][k]; rows past the end are zero.
-__device__ __forceinline__ void load_prof_tile(double *dst, const ScoreSide &s, long long r0) {
-    for (int idx = threadIdx.x; idx < kTile * MCG_NPROF; idx += kPairThreads) {
-        const int r = idx / MCG_NPROF;
-        const int k = idx - r * MCG_NPROF;
-        double v = 0.0;
-        if (r0 + r < s.n) {
-            const long long row = s.index ? s.index[r0 + r] : (r0 + r);
-            v = s.prof[row * MCG_NPROF + k];
-        }
-        dst[k * kTile + (r ^ (k & 15))] = v;
+// ||row||^2 of a [rows,136] table, one warp per row (the dot-product form of the distance).
+__global__ void row_norms_kernel(const double *__restrict__ prof, long long rows,
+                                 double *__restrict__ norm) {
+    const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double *p = prof + row * MCG_NPROF;
+    double acc = 0.0;
+    for (int k = lane; k < MCG_NPROF; k += 32) acc = fma(p[k], p[k], acc);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) norm[row] = acc;
+}
+
+// ---- the pair kernel ---------------------------------------------------------------------
+// Shared memory (doubles): Ak[34][64] Bk[34][64]  one k-chunk of both profile tiles,
+//                          CA[12][3][64] CB[12][3][64]  coverage terms of <= 12 samples,
+//                          NA[64] NB[64] squared norms, ET[16] exp table, row ids.
+// 72.9 KB per CTA and <= 128 registers, so two CTAs share an SM: while one stages a chunk
+// the other computes.
+constexpr int kKC = 34;                       // 136 = 4 * 34
+constexpr int kPairSmemDoubles = 2 * kKC * kTile + 2 * kSampleChunk * 3 * kTile + 2 * kTile + 16;
+constexpr size_t kPairSmem = sizeof(double) * kPairSmemDoubles + sizeof(long long) * 2 * kTile;
+
+// dst[kk][r ^ (kk & 15)] = prof[row(r)][k0 + kk]; the XOR makes the transposing store and the
+// strided reads conflict-free.  Rows past the end (id < 0) are zero.
+__device__ __forceinline__ void load_prof_chunk(double *dst, const double *__restrict__ prof,
+                                                const long long *rows, int k0) {
+    for (int idx = threadIdx.x; idx < kTile * kKC; idx += kPairThreads) {
+        const int r = idx / kKC;
+        const int kk = idx - r * kKC;
+        const long long row = rows[r];
+        dst[kk * kTile + (r ^ (kk & 15))] = row >= 0 ? prof[row * MCG_NPROF + k0 + kk] : 0.0;
     }
 }
 
-// dst[s][term][r] for samples [s0, s0+sc); rows past the end get c = 1 (log 0, lgamma 0).
-__device__ __forceinline__ void load_cov_chunk(double *dst, const ScoreSide &s, long long r0,
-                                               int S, int s0, int sc) {
+// dst[q][term][r] for samples [s0, s0+sc); rows past the end get c = 1 (log 0, lgamma 0).
+__device__ __forceinline__ void load_cov_chunk(double *dst, const ScoreSide &s,
+                                               const long long *rows, int S, int s0, int sc) {
     for (int idx = threadIdx.x; idx < kTile * sc; idx += kPairThreads) {
         const int r = idx / sc;
         const int q = idx - r * sc;
         double c = 1.0, lc = 0.0, lg = 0.0;
-        if (r0 + r < s.n) {
-            const long long row = s.index ? s.index[r0 + r] : (r0 + r);
+        const long long row = rows[r];
+        if (row >= 0) {
             const long long off = row * S + s0 + q;
             c = s.cov[off];
             lc = s.logc[off];
@@ -157,14 +205,22 @@ __device__ __forceinline__ void load_cov_chunk(double *dst, const ScoreSide &s, 
     }
 }
 
-template <bool RULE_C>
-__global__ void __launch_bounds__(kPairThreads, 1)
+// RULE_C: rule-C weights / argmin (label_prop_utils.py:308-345), else raw per-pair outputs.
+// DOT: distance from ||u||^2 + ||v||^2 - 2 u.v (136 FMAs per pair) instead of the
+// difference form (272); used whenever the distance itself is not an output.
+template <bool RULE_C, bool DOT>
+__global__ void __launch_bounds__(kPairThreads, 2)
 pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) double sm[];
-    double *As = sm;                              // [136][64]
-    double *Bs = As + MCG_NPROF * kTile;          // [136][64]
-    double *CA = Bs + MCG_NPROF * kTile;          // [16][3][64]
-    double *CB = CA + kSampleChunk * 3 * kTile;   // [16][3][64]
+    double *Ak = sm;
+    double *Bk = Ak + kKC * kTile;
+    double *CA = Bk + kKC * kTile;
+    double *CB = CA + kSampleChunk * 3 * kTile;
+    double *NA = CB + kSampleChunk * 3 * kTile;
+    double *NB = NA + kTile;
+    double *ET = NB + kTile;
+    long long *rowA = reinterpret_cast<long long *>(ET + 16);
+    long long *rowB = rowA + kTile;
 
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;
@@ -172,8 +228,15 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
     const long long n_btiles = (B.n + kTile - 1) / kTile;
     const bool single_chunk = S <= kSampleChunk;
 
-    load_prof_tile(As, A, a0);
-    if (single_chunk) load_cov_chunk(CA, A, a0, S, 0, S);
+    if (tid < 16) ET[tid] = g_exp_table[tid];
+    if (tid < kTile) {
+        long long row = -1;
+        if (a0 + tid < A.n) row = A.index ? A.index[a0 + tid] : (a0 + tid);
+        rowA[tid] = row;
+        NA[tid] = (DOT && row >= 0) ? A.norm[row] : 0.0;
+    }
+    __syncthreads();
+    if (single_chunk) load_cov_chunk(CA, A, rowA, S, 0, S);
 
     double best_w[4];
     int best_i[4];
@@ -183,84 +246,100 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
 
     for (long long bt = blockIdx.y; bt < n_btiles; bt += gridDim.y) {
         const long long b0 = bt * kTile;
-        __syncthreads();   // everyone is done with the previous Bs / CB
-        load_prof_tile(Bs, B, b0);
-        if (single_chunk) load_cov_chunk(CB, B, b0, S, 0, S);
+        __syncthreads();   // everyone is done with the previous tile's NB / rowB / CB
+        if (tid < kTile) {
+            long long row = -1;
+            if (b0 + tid < B.n) row = B.index ? B.index[b0 + tid] : (b0 + tid);
+            rowB[tid] = row;
+            NB[tid] = (DOT && row >= 0) ? B.norm[row] : 0.0;
+        }
         __syncthreads();
+        if (single_chunk) load_cov_chunk(CB, B, rowB, S, 0, S);
 
-        // ---- squared tetramer distance (matching_utils.py:28-29) --------------------
+        // ---- squared tetramer distance (matching_utils.py:28-29), k in four chunks -------
         double acc[4][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
             for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < MCG_NPROF / kKC; ++c) {
+            if (c) __syncthreads();   // the previous chunk has been consumed
+            load_prof_chunk(Ak, A.prof, rowA, c * kKC);
+            load_prof_chunk(Bk, B.prof, rowB, c * kKC);
+            __syncthreads();
 #pragma unroll 2
-        for (int k = 0; k < MCG_NPROF; ++k) {
-            const int sw = k & 15;
-            const double *ar = As + k * kTile + (ti ^ sw);
-            const double *br = Bs + k * kTile + (tj ^ sw);
-            double a[4], b[4];
+            for (int kk = 0; kk < kKC; ++kk) {
+                const int sw = kk & 15;
+                const double *ar = Ak + kk * kTile + (ti ^ sw);
+                const double *br = Bk + kk * kTile + (tj ^ sw);
+                double a[4], b[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { a[e] = ar[16 * e]; b[e] = br[16 * e]; }
+                for (int e = 0; e < 4; ++e) { a[e] = ar[16 * e]; b[e] = br[16 * e]; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        if (DOT) {
+                            acc[e][f] = fma(a[e], b[f], acc[e][f]);
+                        } else {
+                            const double d = a[e] - b[f];
+                            acc[e][f] = fma(d, d, acc[e][f]);
+                        }
+                    }
+            }
+        }
+        if (DOT) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
 #pragma unroll
                 for (int f = 0; f < 4; ++f) {
-                    const double d = a[e] - b[f];
-                    acc[e][f] = fma(d, d, acc[e][f]);
+                    const double d2 = fma(-2.0, acc[e][f], NA[ti + 16 * e] + NB[tj + 16 * f]);
+                    acc[e][f] = d2 > 0.0 ? d2 : 0.0;
                 }
         }
 
-        // ---- Poisson products over the samples, in sample order -----------------------
-        double p1[4][4], p2[4][4];
+        // ---- one column of pairs at a time: Poisson products in sample order, epilogue -----
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f) {
+            double p1[4], p2[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int f = 0; f < 4; ++f) { p1[e][f] = 1.0; p2[e][f] = 1.0; }
-        for (int s0 = 0; s0 < S; s0 += kSampleChunk) {
-            const int sc = min(kSampleChunk, S - s0);
-            if (!single_chunk) {
-                __syncthreads();
-                load_cov_chunk(CA, A, a0, S, s0, sc);
-                load_cov_chunk(CB, B, b0, S, s0, sc);
-                __syncthreads();
-            }
-            for (int q = 0; q < sc; ++q) {
-                const double *ca = CA + q * 3 * kTile + ti;
-                const double *cb = CB + q * 3 * kTile + tj;
-                double ac[4], al[4], ag[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    ac[e] = ca[16 * e];
-                    al[e] = ca[kTile + 16 * e];
-                    ag[e] = ca[2 * kTile + 16 * e];
+            for (int e = 0; e < 4; ++e) { p1[e] = 1.0; p2[e] = 1.0; }
+            for (int s0 = 0; s0 < S; s0 += kSampleChunk) {
+                const int sc = min(kSampleChunk, S - s0);
+                if (!single_chunk) {
+                    __syncthreads();
+                    load_cov_chunk(CA, A, rowA, S, s0, sc);
+                    load_cov_chunk(CB, B, rowB, S, s0, sc);
+                    __syncthreads();
                 }
-#pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const double bc = cb[16 * f];
-                    const double bl = cb[kTile + 16 * f];
-                    const double bg = cb[2 * kTile + 16 * f];
+#pragma unroll 2
+                for (int q = 0; q < sc; ++q) {
+                    const double *ca = CA + q * 3 * kTile + ti;
+                    const double *cb = CB + q * 3 * kTile + tj + 16 * f;
+                    const double bc = cb[0], bl = cb[kTile], bg = cb[2 * kTile];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
+                        const double ac = ca[16 * e];
+                        const double al = ca[kTile + 16 * e];
+                        const double ag = ca[2 * kTile + 16 * e];
                         // cov1 = the A row, cov2 = the B row (matching_utils.py:48-54)
-                        p1[e][f] = __dmul_rn(p1[e][f], poisson_term(ac[e], ag[e], bc, bl));
-                        p2[e][f] = __dmul_rn(p2[e][f], poisson_term(bc, bg, ac[e], al[e]));
+                        p1[e] = __dmul_rn(p1[e], poisson_term(ac, ag, bc, bl, ET));
+                        p2[e] = __dmul_rn(p2[e], poisson_term(bc, bg, ac, al, ET));
                     }
                 }
             }
-        }
-
-        // ---- per-pair epilogue --------------------------------------------------------------
+            const long long bc = b0 + tj + 16 * f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const long long ar = a0 + ti + 16 * e;
-#pragma unroll
-            for (int f = 0; f < 4; ++f) {
-                const long long bc = b0 + tj + 16 * f;
+            for (int e = 0; e < 4; ++e) {
+                const long long ar = a0 + ti + 16 * e;
+                // f is a runtime index: pick acc[e][f] without making acc[] addressable
+                const double d2 = f == 0 ? acc[e][0] : f == 1 ? acc[e][1]
+                                : f == 2 ? acc[e][2] : acc[e][3];
                 if (ar >= A.n || bc >= B.n) continue;
-                const double dist = sqrt(acc[e][f]);
+                const double dist = sqrt(d2);
                 const double pc = comp_prob_dev(dist);
-                const double pv = p1[e][f] < p2[e][f] ? p1[e][f] : p2[e][f];
+                const double pv = p1[e] < p2[e] ? p1[e] : p2[e];
                 if (pc != pc) domain_error = true;
                 const bool valid = __dmul_rn(pc, pv) > 0.0;
                 const double lp = valid ? neg_log10_sum(pc, pv) : MCG_MAX_WEIGHT;
@@ -391,8 +470,8 @@ __global__ void cov_prob_kernel(const double *__restrict__ c1, const double *__r
     double p1 = 1.0, p2 = 1.0;
     for (int s = 0; s < S; ++s) {
         const double a = c1[i * S + s], b = c2[i * S + s];
-        p1 = __dmul_rn(p1, poisson_term(a, lgamma_cpython(__dadd_rn(a, 1.0)), b, log(b)));
-        p2 = __dmul_rn(p2, poisson_term(b, lgamma_cpython(__dadd_rn(b, 1.0)), a, log(a)));
+        p1 = __dmul_rn(p1, poisson_term(a, lgamma_cpython(__dadd_rn(a, 1.0)), b, log(b), g_exp_table));
+        p2 = __dmul_rn(p2, poisson_term(b, lgamma_cpython(__dadd_rn(b, 1.0)), a, log(a), g_exp_table));
     }
     out[i] = p1 < p2 ? p1 : p2;
 }
@@ -432,13 +511,20 @@ static int ensure_gauss(mcg_ctx *ctx) {
     g.ln10 = log(10.0);
     MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss, &g, sizeof g, 0, cudaMemcpyHostToDevice,
                                           ctx->stream));
+    double table[16];
+    for (int j = 0; j < 16; ++j) table[j] = exp2(j / 16.0);
+    MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(g_exp_table, table, sizeof table, 0,
+                                          cudaMemcpyHostToDevice, ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kPairSmem)));
-    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kPairSmem)));
+    const int smem = static_cast<int>(kPairSmem);
+    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<true, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<true, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<false, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<false, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (ctx->device < 64) ready[ctx->device] = true;
     return MCG_OK;
 }
@@ -455,6 +541,13 @@ int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam,
     return MCG_OK;
 }
 
+int mcg_k_row_norms(mcg_ctx *ctx, const double *d_prof, int64_t rows, double *d_norm) {
+    if (rows == 0) return MCG_OK;
+    row_norms_kernel<<<blocks_for(rows * 32, 256), 256, 0, ctx->stream>>>(d_prof, rows, d_norm);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
 int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samples,
                 const ScoreOut &out, int32_t *d_status) {
     MCG_TRY(ensure_gauss(ctx));
@@ -464,9 +557,16 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
     const long long b_tiles = (b.n + kTile - 1) / kTile;
     if (a_tiles > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many query rows");
     dim3 grid(static_cast<unsigned>(a_tiles), 1, 1);
+    // the dot-product form needs the squared norms of both sides and is used whenever the
+    // distance itself is not reported
+    const bool dot = out.dist == nullptr && a.norm != nullptr && b.norm != nullptr;
     if (rule_c) {
-        pair_kernel<true><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(a, b, n_samples, out,
-                                                                          d_status);
+        if (dot)
+            pair_kernel<true, true><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
+                a, b, n_samples, out, d_status);
+        else
+            pair_kernel<true, false><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
+                a, b, n_samples, out, d_status);
     } else {
         // few query tiles: spread the B tiles over grid.y to fill the SMs
         long long gy = (2LL * ctx->sm_count + a_tiles - 1) / a_tiles;
@@ -474,8 +574,12 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
         if (gy < 1) gy = 1;
         if (gy > 65535) gy = 65535;
         grid.y = static_cast<unsigned>(gy);
-        pair_kernel<false><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(a, b, n_samples, out,
-                                                                           d_status);
+        if (dot)
+            pair_kernel<false, true><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
+                a, b, n_samples, out, d_status);
+        else
+            pair_kernel<false, false><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
+                a, b, n_samples, out, d_status);
     }
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
