@@ -77,11 +77,12 @@ int mcg_check_status(mcg_ctx *ctx) {
     MCG_CUDA(ctx, cudaMemcpyAsync(flags, ctx->status.p, sizeof flags, cudaMemcpyDeviceToHost,
                                   ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (flags[0] & 1) {
-        cudaMemsetAsync(ctx->status.p, 0, sizeof flags, ctx->stream);
+    if (flags[0]) cudaMemsetAsync(ctx->status.p, 0, sizeof flags, ctx->stream);
+    if (flags[0] & 2)
+        return mcg_fail(ctx, MCG_ERR_ARG, "coverage values must be finite (NaN or inf found)");
+    if (flags[0] & 1)
         return mcg_fail(ctx, MCG_ERR_DOMAIN,
                         "float division by zero (get_comp_probability: both Gaussians underflow)");
-    }
     return MCG_OK;
 }
 
@@ -403,7 +404,7 @@ extern "C" int mcg_load_coverage(mcg_ctx *ctx, const double *cov, int64_t n, int
     MCG_ENTER(ctx);
     MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples));
     MCG_TRY(cov_terms_locked(ctx));
-    return sync(ctx);
+    return mcg_check_status(ctx);
 }
 
 extern "C" int mcg_get_coverage_terms(mcg_ctx *ctx, double *cov, double *logc, double *lgam) {

@@ -89,60 +89,112 @@ __device__ __forceinline__ double normpdf_dev(double x, double mean, double two_
 
 // matching_utils.py:36-39.  NaN when both Gaussians underflow (the reference raises
 // ZeroDivisionError there); the caller turns that into MCG_ERR_DOMAIN.
-__device__ __forceinline__ double comp_prob_dev(double d) {
+__device__ __noinline__ double comp_prob_dev(double d) {
     const double gi = normpdf_dev(d, 0.0, c_gauss.two_var_intra, c_gauss.denom_intra);
     const double ge = normpdf_dev(d, c_gauss.mu_inter, c_gauss.two_var_inter,
                                   c_gauss.denom_inter);
     return __ddiv_rn(gi, __dadd_rn(gi, ge));
 }
 
-// ---- exp for the Poisson terms -------------------------------------------------------------
+// ---- fast exp / log for the hot loop -----------------------------------------------------------
 // exp(x) = 2^(k/16) * e^r with k = round(16 x / ln 2), |r| <= ln2/32: a 16-entry table of
 // 2^(j/16) (one 128-byte shared-memory wavefront, so 32 lanes with 32 different arguments
-// never conflict) times a degree-7 Taylor polynomial (truncation 1.2e-18), exponent added
-// as an integer.  ~12 FP64 instructions against ~28 for the library exp(); < 2 ulp.
-// Arguments below -100 are clamped: the callers floor the result at 1e-10 anyway
-// (matching_utils.py:56-60), and the clamp keeps the exponent arithmetic in the normal range.
+// never conflict) times a degree-7 Taylor polynomial (truncation 1.2e-18), the exponent added
+// as an integer.  ~11 FP64 instructions against ~28 for the library exp(); < 2 ulp.
+// Valid for |x| < 700 (result stays a normal number); callers guarantee the range.
+//
+// log(x) = e ln2 - log(rcp_j) + log1p(m rcp_j - 1): j = top six mantissa bits, rcp_j ~ 1/c_j
+// with c_j the midpoint of the j-th mantissa interval, |m rcp_j - 1| <= 2^-7, degree-7 series.
+// Valid for normal positive x; ~13 FP64 instructions against ~45 for the library log().
 __device__ double g_exp_table[16];
+__device__ double g_log_table[128];   // [0..63] rcp_j, [64..127] -log(rcp_j)
 
-__device__ __forceinline__ double exp_tab16(double x, const double *__restrict__ table) {
-    const double xc = x < -100.0 ? -100.0 : x;
-    const double kd = fma(xc, 23.083120654223414, 6755399441055744.0);   // 16/ln2, 1.5*2^52
+struct MathConst {
+    double inv_ln2_16, magic, ln2_16_hi, ln2_16_lo;   // exp range reduction
+    double e7, e6, e5, e4, e3;                        // 1/5040 .. 1/6 (0.5 is an immediate)
+    double ln2_hi, ln2_lo;                            // log: e * ln2 in two parts
+    double l7, l6, l5, l4, l3;                        // 1/7, -1/6, 1/5, -1/4, 1/3
+    double log_floor;                                 // log(1e-10), matching_utils.py:14
+    double inv_two_var_intra, inv_denom_intra, inv_two_var_inter, inv_denom_inter, inv_ln10;
+};
+__constant__ MathConst c_math;
+
+__device__ __forceinline__ double exp_core(double x, const double *__restrict__ table) {
+    const double kd = fma(x, c_math.inv_ln2_16, c_math.magic);
     const int ki = __double2loint(kd);
-    const double kf = kd - 6755399441055744.0;
-    double r = fma(kf, -0x1.62e42ff000000p-5, xc);    // ln2/16, high 32 bits
-    r = fma(kf, 0x1.718432a1b0e26p-39, r);            // minus the low part
-    double q = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-    q = fma(q, r, 1.0 / 120.0);
-    q = fma(q, r, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
+    const double kf = kd - c_math.magic;
+    double r = fma(kf, c_math.ln2_16_hi, x);
+    r = fma(kf, c_math.ln2_16_lo, r);
+    double q = fma(r, c_math.e7, c_math.e6);
+    q = fma(q, r, c_math.e5);
+    q = fma(q, r, c_math.e4);
+    q = fma(q, r, c_math.e3);
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);
     const double t = table[ki & 15];
     const double res = fma(t, em1, t);
-    const int hi = __double2hiint(res) + ((ki >> 4) << 20);
+    const int hi = __double2hiint(res) + ((ki & ~15) << 16);   // += (k >> 4) << 20
     return __hiloint2double(hi, __double2loint(res));
 }
 
-// One sample of matching_utils.py:48-57: exp(c1*log(c2) - lgamma(c1+1) - c2), floored.
+__device__ __noinline__ double log_slow(double x) { return log(x); }
+
+__device__ __forceinline__ double log_core(double x, const double *__restrict__ table) {
+    const int hi = __double2hiint(x);
+    if (hi < 0x00100000 || hi >= 0x7ff00000) return log_slow(x);   // denormal, 0, < 0, inf, nan
+    const int j = (hi >> 14) & 63;
+    const double e = static_cast<double>((hi >> 20) - 1023);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double r = fma(m, table[j], -1.0);
+    double q = fma(r, c_math.l7, c_math.l6);
+    q = fma(q, r, c_math.l5);
+    q = fma(q, r, c_math.l4);
+    q = fma(q, r, c_math.l3);
+    q = fma(q, r, -0.5);
+    const double l1p = fma(q, r * r, r);
+    const double head = fma(e, c_math.ln2_hi, table[64 + j]);
+    return head + fma(e, c_math.ln2_lo, l1p);
+}
+
+// One sample of matching_utils.py:48-57: max(exp(c1*log(c2) - lgamma(c1+1) - c2), 1e-10).  The
+// floor is applied to the exponent (exp is monotonic), so no exp argument leaves [-23.03, ~0].
+__device__ __forceinline__ double poisson_exponent(double c1, double lg1, double c2,
+                                                   double logc2) {
+    const double x = __dsub_rn(__dsub_rn(__dmul_rn(c1, logc2), lg1), c2);
+    return x < c_math.log_floor ? c_math.log_floor : x;
+}
 __device__ __forceinline__ double poisson_term(double c1, double lg1, double c2, double logc2,
                                                const double *__restrict__ table) {
-    double p = exp_tab16(__dsub_rn(__dsub_rn(__dmul_rn(c1, logc2), lg1), c2), table);
-    if (p < 1e-10) p = 1e-10;
-    return p;
+    return exp_core(poisson_exponent(c1, lg1, c2, logc2), table);
 }
 
-// -(log(pc, 10) + log(pv, 10)) with math.log(x, 10) = log(x) / log(10)
-__device__ __forceinline__ double neg_log10_sum(double pc, double pv) {
-    return -__dadd_rn(__ddiv_rn(log(pc), c_gauss.ln10), __ddiv_rn(log(pv), c_gauss.ln10));
+// prob_comp from the squared distance (matching_utils.py:21-39).  Fast path: table exp and
+// reciprocal multiplies (a few ulp, far inside the 1e-9 bar).  When a Gaussian is about to
+// underflow (exponent below -700) the reference's own operation sequence is used instead, so
+// that the denormal / exact-zero results that decide prob_product > 0 come out the same way.
+__device__ __forceinline__ double comp_prob_fast(double d2, const double *__restrict__ table) {
+    const double d = sqrt(d2);
+    const double dx = __dsub_rn(d, c_gauss.mu_inter);
+    const double ai = -d2 * c_math.inv_two_var_intra;
+    const double ae = -(dx * dx) * c_math.inv_two_var_inter;
+    // exp() underflows to exactly 0 below -745.14: prob_comp is then 0 / (0 + ge) = 0
+    if (ai < -746.0 && ae >= -700.0) return 0.0;
+    if (ai < -700.0 || ae < -700.0 || !(ai <= 0.0)) return comp_prob_dev(d);
+    const double gi = exp_core(ai, table) * c_math.inv_denom_intra;
+    const double ge = exp_core(ae, table) * c_math.inv_denom_inter;
+    return __ddiv_rn(gi, gi + ge);
 }
+
 
 // ---- coverage terms --------------------------------------------------------------------
+// status bit 2: a coverage value is NaN or infinite (the fast exp path assumes finite inputs).
 __global__ void cov_terms_kernel(double *__restrict__ cov, double *__restrict__ logc,
-                                 double *__restrict__ lgam, long long count) {
+                                 double *__restrict__ lgam, long long count,
+                                 int32_t *__restrict__ status) {
     const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i >= count) return;
     double c = cov[i];
+    if (!(fabs(c) <= DBL_MAX)) atomicOr(status, 2);
     if (c < 0.0001) c = 0.0001;   // feature_utils.py:152-153
     cov[i] = c;
     logc[i] = log(c);
@@ -164,24 +216,37 @@ __global__ void row_norms_kernel(const double *__restrict__ prof, long long rows
 }
 
 // ---- the pair kernel ---------------------------------------------------------------------
-// Shared memory (doubles): Ak[34][64] Bk[34][64]  one k-chunk of both profile tiles,
-//                          CA[12][3][64] CB[12][3][64]  coverage terms of <= 12 samples,
-//                          NA[64] NB[64] squared norms, ET[16] exp table, row ids.
-// 72.9 KB per CTA and <= 128 registers, so two CTAs share an SM: while one stages a chunk
-// the other computes.
+// Shared memory (doubles): stage[2] x { Ak[34][64], Bk[34][64] }  k-chunks of both profile
+//                          tiles, filled with cp.async two chunks ahead of their use;
+//                          CA[12][3][64] CB[12][3][64]  coverage terms of <= 12 samples;
+//                          NA[64] NB[2][64] squared norms; exp / log tables; row ids.
+// ~107 KB per CTA and <= 128 registers: two CTAs share an SM.
 constexpr int kKC = 34;                       // 136 = 4 * 34
-constexpr int kPairSmemDoubles = 2 * kKC * kTile + 2 * kSampleChunk * 3 * kTile + 2 * kTile + 16;
-constexpr size_t kPairSmem = sizeof(double) * kPairSmemDoubles + sizeof(long long) * 2 * kTile;
+constexpr int kChunkDoubles = kKC * kTile;    // one side of one stage
+constexpr int kPairSmemDoubles = 4 * kChunkDoubles + 2 * kSampleChunk * 3 * kTile + 3 * kTile +
+                                 16 + 128;
+constexpr size_t kPairSmem = sizeof(double) * kPairSmemDoubles + sizeof(long long) * 3 * kTile;
 
-// dst[kk][r ^ (kk & 15)] = prof[row(r)][k0 + kk]; the XOR makes the transposing store and the
-// strided reads conflict-free.  Rows past the end (id < 0) are zero.
-__device__ __forceinline__ void load_prof_chunk(double *dst, const double *__restrict__ prof,
-                                                const long long *rows, int k0) {
+__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// dst[kk][r ^ (kk & 15)] <- prof[row(r)][k0 + kk], asynchronously; the XOR makes the
+// transposing store and the strided reads conflict-free.  Rows past the end are zero.
+__device__ __forceinline__ void stage_prof_chunk(double *dst, const double *__restrict__ prof,
+                                                 const long long *rows, int k0) {
     for (int idx = threadIdx.x; idx < kTile * kKC; idx += kPairThreads) {
         const int r = idx / kKC;
         const int kk = idx - r * kKC;
         const long long row = rows[r];
-        dst[kk * kTile + (r ^ (kk & 15))] = row >= 0 ? prof[row * MCG_NPROF + k0 + kk] : 0.0;
+        double *d = dst + kk * kTile + (r ^ (kk & 15));
+        if (row >= 0) cp_async8(d, prof + row * MCG_NPROF + k0 + kk);
+        else *d = 0.0;
     }
 }
 
@@ -205,38 +270,59 @@ __device__ __forceinline__ void load_cov_chunk(double *dst, const ScoreSide &s,
     }
 }
 
+__device__ __forceinline__ void tile_rows(long long *rows, double *norms, const ScoreSide &s,
+                                          long long r0, bool want_norm) {
+    const int tid = threadIdx.x;
+    if (tid < kTile) {
+        long long row = -1;
+        if (r0 + tid < s.n) row = s.index ? s.index[r0 + tid] : (r0 + tid);
+        rows[tid] = row;
+        norms[tid] = (want_norm && row >= 0) ? s.norm[row] : 0.0;
+    }
+}
+
 // RULE_C: rule-C weights / argmin (label_prop_utils.py:308-345), else raw per-pair outputs.
 // DOT: distance from ||u||^2 + ||v||^2 - 2 u.v (136 FMAs per pair) instead of the
 // difference form (272); used whenever the distance itself is not an output.
-template <bool RULE_C, bool DOT>
+// LOGSUM (S <= 30): the product of the floored Poisson terms is carried as the sum of their
+// floored exponents, prod_s max(e^x_s, 1e-10) = exp(sum_s max(x_s, log 1e-10)): one exp per
+// pair instead of 2 S.  With S <= 30 the sum stays above -691, so neither running product can
+// underflow in the reference either and the two forms agree to ~S ulp.  For S > 30 the
+// reference's products reach the denormal range, where its sequential rounding (and the
+// exact zero that decides prob_product > 0) can only be reproduced by multiplying in order.
+template <bool RULE_C, bool DOT, bool LOGSUM>
 __global__ void __launch_bounds__(kPairThreads, 2)
 pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) double sm[];
-    double *Ak = sm;
-    double *Bk = Ak + kKC * kTile;
-    double *CA = Bk + kKC * kTile;
+    double *stage = sm;                                   // [2][2][34][64]
+    double *CA = stage + 4 * kChunkDoubles;
     double *CB = CA + kSampleChunk * 3 * kTile;
     double *NA = CB + kSampleChunk * 3 * kTile;
-    double *NB = NA + kTile;
-    double *ET = NB + kTile;
-    long long *rowA = reinterpret_cast<long long *>(ET + 16);
-    long long *rowB = rowA + kTile;
+    double *NB = NA + kTile;                              // [2][64]
+    double *ET = NB + 2 * kTile;                          // 16
+    double *LT = ET + 16;                                 // 128
+    long long *rowA = reinterpret_cast<long long *>(LT + 128);
+    long long *rowB = rowA + kTile;                       // [2][64]
 
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;
     const long long a0 = static_cast<long long>(blockIdx.x) * kTile;
     const long long n_btiles = (B.n + kTile - 1) / kTile;
     const bool single_chunk = S <= kSampleChunk;
+    constexpr int kChunks = MCG_NPROF / kKC;
 
     if (tid < 16) ET[tid] = g_exp_table[tid];
-    if (tid < kTile) {
-        long long row = -1;
-        if (a0 + tid < A.n) row = A.index ? A.index[a0 + tid] : (a0 + tid);
-        rowA[tid] = row;
-        NA[tid] = (DOT && row >= 0) ? A.norm[row] : 0.0;
-    }
+    if (tid < 128) LT[tid] = g_log_table[tid];
+    tile_rows(rowA, NA, A, a0, DOT);
+    long long bt = blockIdx.y;
+    if (bt < n_btiles) tile_rows(rowB, NB, B, bt * kTile, DOT);
     __syncthreads();
     if (single_chunk) load_cov_chunk(CA, A, rowA, S, 0, S);
+    if (bt < n_btiles) {   // chunk 0 of the first tile
+        stage_prof_chunk(stage, A.prof, rowA, 0);
+        stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB, 0);
+    }
+    cp_async_commit();
 
     double best_w[4];
     int best_i[4];
@@ -244,17 +330,16 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
     for (int e = 0; e < 4; ++e) { best_w[e] = 0.0; best_i[e] = -1; }
     bool domain_error = false;
 
-    for (long long bt = blockIdx.y; bt < n_btiles; bt += gridDim.y) {
+    for (int it = 0; bt < n_btiles; bt += gridDim.y, ++it) {
+        const int cur = it & 1;
         const long long b0 = bt * kTile;
-        __syncthreads();   // everyone is done with the previous tile's NB / rowB / CB
-        if (tid < kTile) {
-            long long row = -1;
-            if (b0 + tid < B.n) row = B.index ? B.index[b0 + tid] : (b0 + tid);
-            rowB[tid] = row;
-            NB[tid] = (DOT && row >= 0) ? B.norm[row] : 0.0;
-        }
-        __syncthreads();
-        if (single_chunk) load_cov_chunk(CB, B, rowB, S, 0, S);
+        const long long *rows_b = rowB + cur * kTile;
+        const double *norm_b = NB + cur * kTile;
+        const long long bt_next = bt + gridDim.y;
+        // rows of the next tile (its chunk 0 is staged below, during this tile's phase 2)
+        if (bt_next < n_btiles) tile_rows(rowB + (cur ^ 1) * kTile, NB + (cur ^ 1) * kTile, B,
+                                          bt_next * kTile, DOT);
+        if (single_chunk) load_cov_chunk(CB, B, rows_b, S, 0, S);
 
         // ---- squared tetramer distance (matching_utils.py:28-29), k in four chunks -------
         double acc[4][4];
@@ -263,11 +348,19 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
 #pragma unroll
             for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
 #pragma unroll 1
-        for (int c = 0; c < MCG_NPROF / kKC; ++c) {
-            if (c) __syncthreads();   // the previous chunk has been consumed
-            load_prof_chunk(Ak, A.prof, rowA, c * kKC);
-            load_prof_chunk(Bk, B.prof, rowB, c * kKC);
-            __syncthreads();
+        for (int c = 0; c < kChunks; ++c) {
+            if (c + 1 < kChunks) {
+                double *nxt = stage + ((c + 1) & 1) * 2 * kChunkDoubles;
+                stage_prof_chunk(nxt, A.prof, rowA, (c + 1) * kKC);
+                stage_prof_chunk(nxt + kChunkDoubles, B.prof, rows_b, (c + 1) * kKC);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();   // chunk c has landed for everyone
+            const double *Ak = stage + (c & 1) * 2 * kChunkDoubles;
+            const double *Bk = Ak + kChunkDoubles;
 #pragma unroll 2
             for (int kk = 0; kk < kKC; ++kk) {
                 const int sw = kk & 15;
@@ -288,13 +381,19 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                         }
                     }
             }
+            __syncthreads();   // stage c & 1 may be refilled
         }
+        if (bt_next < n_btiles) {   // chunk 0 of the next tile flies during phase 2
+            stage_prof_chunk(stage, A.prof, rowA, 0);
+            stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB + (cur ^ 1) * kTile, 0);
+        }
+        cp_async_commit();
         if (DOT) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
 #pragma unroll
                 for (int f = 0; f < 4; ++f) {
-                    const double d2 = fma(-2.0, acc[e][f], NA[ti + 16 * e] + NB[tj + 16 * f]);
+                    const double d2 = fma(-2.0, acc[e][f], NA[ti + 16 * e] + norm_b[tj + 16 * f]);
                     acc[e][f] = d2 > 0.0 ? d2 : 0.0;
                 }
         }
@@ -304,13 +403,13 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
         for (int f = 0; f < 4; ++f) {
             double p1[4], p2[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { p1[e] = 1.0; p2[e] = 1.0; }
+            for (int e = 0; e < 4; ++e) { p1[e] = LOGSUM ? 0.0 : 1.0; p2[e] = p1[e]; }
             for (int s0 = 0; s0 < S; s0 += kSampleChunk) {
                 const int sc = min(kSampleChunk, S - s0);
                 if (!single_chunk) {
                     __syncthreads();
                     load_cov_chunk(CA, A, rowA, S, s0, sc);
-                    load_cov_chunk(CB, B, rowB, S, s0, sc);
+                    load_cov_chunk(CB, B, rows_b, S, s0, sc);
                     __syncthreads();
                 }
 #pragma unroll 2
@@ -324,8 +423,13 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                         const double al = ca[kTile + 16 * e];
                         const double ag = ca[2 * kTile + 16 * e];
                         // cov1 = the A row, cov2 = the B row (matching_utils.py:48-54)
-                        p1[e] = __dmul_rn(p1[e], poisson_term(ac, ag, bc, bl, ET));
-                        p2[e] = __dmul_rn(p2[e], poisson_term(bc, bg, ac, al, ET));
+                        if (LOGSUM) {
+                            p1[e] += poisson_exponent(ac, ag, bc, bl);
+                            p2[e] += poisson_exponent(bc, bg, ac, al);
+                        } else {
+                            p1[e] = __dmul_rn(p1[e], poisson_term(ac, ag, bc, bl, ET));
+                            p2[e] = __dmul_rn(p2[e], poisson_term(bc, bg, ac, al, ET));
+                        }
                     }
                 }
             }
@@ -337,12 +441,16 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                 const double d2 = f == 0 ? acc[e][0] : f == 1 ? acc[e][1]
                                 : f == 2 ? acc[e][2] : acc[e][3];
                 if (ar >= A.n || bc >= B.n) continue;
-                const double dist = sqrt(d2);
-                const double pc = comp_prob_dev(dist);
-                const double pv = p1[e] < p2[e] ? p1[e] : p2[e];
+                const double pc = comp_prob_fast(d2, ET);
+                const double pmin = p1[e] < p2[e] ? p1[e] : p2[e];
+                const double pv = LOGSUM ? exp_core(pmin, ET) : pmin;
                 if (pc != pc) domain_error = true;
                 const bool valid = __dmul_rn(pc, pv) > 0.0;
-                const double lp = valid ? neg_log10_sum(pc, pv) : MCG_MAX_WEIGHT;
+                double lp = MCG_MAX_WEIGHT;
+                if (valid) {   // -(log(pc, 10) + log(pv, 10))
+                    const double log_pv = LOGSUM ? pmin : log_core(pv, LT);
+                    lp = -(log_core(pc, LT) + log_pv) * c_math.inv_ln10;
+                }
                 const long long o = ar * B.n + bc;
                 if (RULE_C) {
                     // label_prop_utils.py:331-337: log_prob stays 0 unless the product is
@@ -355,14 +463,16 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                         best_i[e] = bi;
                     }
                 } else {
-                    if (out.dist) out.dist[o] = dist;
+                    if (out.dist) out.dist[o] = sqrt(d2);
                     if (out.pc) out.pc[o] = pc;
                     if (out.pv) out.pv[o] = pv;
                     if (out.lp) out.lp[o] = lp;
                 }
             }
         }
+        __syncthreads();   // CB / the other rowB slot are rewritten at the top of the next tile
     }
+    cp_async_wait<0>();
 
     if (domain_error) atomicOr(status, 1);
 
@@ -497,6 +607,16 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 }  // namespace
 
 // ---- launchers -------------------------------------------------------------------------------
+typedef void (*pair_fn)(ScoreSide, ScoreSide, int, ScoreOut, int32_t *);
+static pair_fn pair_variant(bool rule_c, bool dot, bool logsum) {
+    if (rule_c) {
+        if (dot) return logsum ? pair_kernel<true, true, true> : pair_kernel<true, true, false>;
+        return logsum ? pair_kernel<true, false, true> : pair_kernel<true, false, false>;
+    }
+    if (dot) return logsum ? pair_kernel<false, true, true> : pair_kernel<false, true, false>;
+    return logsum ? pair_kernel<false, false, true> : pair_kernel<false, false, false>;
+}
+
 static int ensure_gauss(mcg_ctx *ctx) {
     static bool ready[64] = {};
     if (ctx->device < 64 && ready[ctx->device]) return MCG_OK;
@@ -515,16 +635,36 @@ static int ensure_gauss(mcg_ctx *ctx) {
     for (int j = 0; j < 16; ++j) table[j] = exp2(j / 16.0);
     MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(g_exp_table, table, sizeof table, 0,
                                           cudaMemcpyHostToDevice, ctx->stream));
+    double ltab[128];
+    for (int j = 0; j < 64; ++j) {
+        const double rcp = 1.0 / (1.0 + (j + 0.5) / 64.0);
+        ltab[j] = rcp;
+        ltab[64 + j] = static_cast<double>(-logl(static_cast<long double>(rcp)));
+    }
+    MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(g_log_table, ltab, sizeof ltab, 0,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    MathConst m;
+    m.inv_ln2_16 = 23.083120654223414;          // 16 / ln 2
+    m.magic = 6755399441055744.0;               // 1.5 * 2^52
+    m.ln2_16_hi = -0x1.62e42ff000000p-5;        // -(ln2/16), high 32 bits
+    m.ln2_16_lo = 0x1.718432a1b0e26p-39;        // minus the low part
+    m.e7 = 1.0 / 5040.0; m.e6 = 1.0 / 720.0; m.e5 = 1.0 / 120.0; m.e4 = 1.0 / 24.0;
+    m.e3 = 1.0 / 6.0;
+    m.ln2_hi = 0x1.62e42fefa3800p-1;            // ln2 with 11 trailing zero bits
+    m.ln2_lo = 0x1.ef35793c76730p-45;
+    m.l7 = 1.0 / 7.0; m.l6 = -1.0 / 6.0; m.l5 = 1.0 / 5.0; m.l4 = -1.0 / 4.0; m.l3 = 1.0 / 3.0;
+    m.log_floor = log(1e-10);
+    m.inv_two_var_intra = 1.0 / g.two_var_intra;
+    m.inv_denom_intra = 1.0 / g.denom_intra;
+    m.inv_two_var_inter = 1.0 / g.two_var_inter;
+    m.inv_denom_inter = 1.0 / g.denom_inter;
+    m.inv_ln10 = 1.0 / g.ln10;
+    MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_math, &m, sizeof m, 0, cudaMemcpyHostToDevice,
+                                          ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int smem = static_cast<int>(kPairSmem);
-    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<true, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<true, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<false, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MCG_CUDA(ctx, cudaFuncSetAttribute(pair_kernel<false, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int v = 0; v < 8; ++v) MCG_CUDA(ctx, cudaFuncSetAttribute(
+        pair_variant(v & 4, v & 2, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(kPairSmem)));
     if (ctx->device < 64) ready[ctx->device] = true;
     return MCG_OK;
 }
@@ -535,8 +675,8 @@ static inline unsigned blocks_for(long long n, int threads) {
 
 int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam, int64_t count) {
     if (count == 0) return MCG_OK;
-    cov_terms_kernel<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(d_cov, d_logc, d_lgam,
-                                                                      count);
+    cov_terms_kernel<<<blocks_for(count, 256), 256, 0, ctx->stream>>>(
+        d_cov, d_logc, d_lgam, count, ctx->status.as<int32_t>());
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }
@@ -560,27 +700,17 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
     // the dot-product form needs the squared norms of both sides and is used whenever the
     // distance itself is not reported
     const bool dot = out.dist == nullptr && a.norm != nullptr && b.norm != nullptr;
-    if (rule_c) {
-        if (dot)
-            pair_kernel<true, true><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
-                a, b, n_samples, out, d_status);
-        else
-            pair_kernel<true, false><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
-                a, b, n_samples, out, d_status);
-    } else {
+    const bool logsum = n_samples <= 30;
+    if (!rule_c) {
         // few query tiles: spread the B tiles over grid.y to fill the SMs
         long long gy = (2LL * ctx->sm_count + a_tiles - 1) / a_tiles;
         if (gy > b_tiles) gy = b_tiles;
         if (gy < 1) gy = 1;
         if (gy > 65535) gy = 65535;
         grid.y = static_cast<unsigned>(gy);
-        if (dot)
-            pair_kernel<false, true><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
-                a, b, n_samples, out, d_status);
-        else
-            pair_kernel<false, false><<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
-                a, b, n_samples, out, d_status);
     }
+    pair_variant(rule_c, dot, logsum)<<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
+        a, b, n_samples, out, d_status);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }
@@ -634,6 +764,7 @@ int mcg_k_comp_prob(mcg_ctx *ctx, const double *d_dist, double *d_out, int64_t n
 
 int mcg_k_cov_prob(mcg_ctx *ctx, const double *d_c1, const double *d_c2, int64_t n, int S,
                    double *d_out) {
+    MCG_TRY(ensure_gauss(ctx));
     if (n == 0) return MCG_OK;
     cov_prob_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(d_c1, d_c2, n, S, d_out);
     MCG_KERNEL_CHECK(ctx);

@@ -252,7 +252,8 @@ def test_rules_a_b_golden(ctx, score):
         assert_close(got, want[queries])
 
 
-@pytest.mark.parametrize("S,B,n", [(1, 7, 300), (10, 200, 1000), (50, 70, 333), (100, 33, 150)])
+@pytest.mark.parametrize("S,B,n", [(1, 7, 300), (10, 200, 1000), (30, 40, 300), (31, 40, 300),
+                                   (50, 70, 333), (100, 33, 150)])
 def test_rule_c_vs_oracle(ctx, S, B, n):
     """Seeded synthetic contig tables at sizes the oracle finishes in seconds, including
     S > 32 where floor^S underflows and the MAX_WEIGHT / None paths trigger."""
