@@ -24,7 +24,7 @@ namespace {
 
 constexpr int kTile = 64;          // rows per side per CTA tile
 constexpr int kPairThreads = 256;
-constexpr int kSampleChunk = 12;   // samples staged per pass
+constexpr int kSampleChunk = 10;   // samples staged per pass
 
 // matching_utils.py:12-15
 struct GaussConst {
@@ -201,52 +201,83 @@ __global__ void cov_terms_kernel(double *__restrict__ cov, double *__restrict__ 
     lgam[i] = lgamma_cpython(__dadd_rn(c, 1.0));
 }
 
-// ||row||^2 of a [rows,136] table, one warp per row (the dot-product form of the distance).
+// ||row||^2 of a [rows,136] table.  It goes through the same DMMA k-step sequence as the u.v of
+// pair_kernel, so that for two bitwise-equal rows |u|^2 + |v|^2 - 2 u.v is exactly 0, as the
+// reference's difference form is: near d = 0 the inter-species Gaussian is linear in d =
+// sqrt(d^2), and a d^2 of 1e-17 instead of 0 would already move prob_comp by 4e-9.
+// One warp per 8 rows; the diagonal of the 8 x 8 product holds the norms.
 __global__ void row_norms_kernel(const double *__restrict__ prof, long long rows,
                                  double *__restrict__ norm) {
-    const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const double *p = prof + row * MCG_NPROF;
-    double acc = 0.0;
-    for (int k = lane; k < MCG_NPROF; k += 32) acc = fma(p[k], p[k], acc);
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-    if (lane == 0) norm[row] = acc;
+    const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const long long row = warp * 8 + g;
+    if (warp * 8 >= rows) return;
+    const double *p = prof + (row < rows ? row : rows - 1) * MCG_NPROF + t;
+    double c0 = 0.0, c1 = 0.0;
+    for (int k0 = 0; k0 < MCG_NPROF; k0 += 4) {
+        const double a = p[k0];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(a));
+    }
+    // lane (g, t) holds C[g][2t] and C[g][2t+1]
+    if (row < rows) {
+        if (g == 2 * t) norm[row] = c0;
+        if (g == 2 * t + 1) norm[row] = c1;
+    }
 }
 
 // ---- the pair kernel ---------------------------------------------------------------------
-// Shared memory (doubles): stage[2] x { Ak[34][64], Bk[34][64] }  k-chunks of both profile
-//                          tiles, filled with cp.async two chunks ahead of their use;
-//                          CA[12][3][64] CB[12][3][64]  coverage terms of <= 12 samples;
-//                          NA[64] NB[2][64] squared norms; exp / log tables; row ids.
-// ~107 KB per CTA and <= 128 registers: two CTAs share an SM.
-constexpr int kKC = 34;                       // 136 = 4 * 34
-constexpr int kChunkDoubles = kKC * kTile;    // one side of one stage
+// A CTA (8 warps) owns 64 "A" rows (contigs to score) and walks the "B" rows (bin centroids, or
+// member contigs for rules A/B) in tiles of 64.
+//
+//   distance  u.v for the 64 x 64 pairs as an FP64 GEMM on mma.sync.m8n8k4 (DMMA): the FP64 units
+//             deliver the same FLOP rate through DMMA as through DFMA (measured 37 TFLOP/s
+//             either way, and no more when mixed), but one DMMA issues 256 FMAs, so the
+//             contraction stops being issue / shared-load bound.  Warp w holds the 16 x 32
+//             block (rows 16*(w/2).., columns 32*(w%2)..) as 2 x 4 accumulator fragments;
+//             both operand tiles sit in shared memory as [row][k] with a pitch of 36 doubles,
+//             which makes every fragment load hit 16 distinct bank pairs twice (the minimum
+//             for 256 bytes).  k is staged in chunks of 32 with 16-byte cp.async, two chunks
+//             in flight, and the first chunk of the next B tile flies during phase 2.
+//             d^2 = |u|^2 + |v|^2 - 2 u.v from precomputed norms.
+//   phase 2   every lane then owns 2 rows x 8 columns (its accumulator fragments) and runs the
+//             Poisson terms over the samples for 4 pairs at a time, then the epilogue.
+//
+// 112 KB of shared memory per CTA and <= 128 registers: two CTAs share an SM.
+constexpr int kKC = 32;                       // k-chunk (8 DMMA k-steps); 136 = 4 * 32 + 8
+constexpr int kPitch = kKC + 4;               // pitch = 4 mod 16 doubles: conflict-free fragments
+constexpr int kChunkDoubles = kTile * kPitch; // one side of one stage
 constexpr int kPairSmemDoubles = 4 * kChunkDoubles + 2 * kSampleChunk * 3 * kTile + 3 * kTile +
-                                 16 + 128;
-constexpr size_t kPairSmem = sizeof(double) * kPairSmemDoubles + sizeof(long long) * 3 * kTile;
+                                 16 + 128 + 2 * kTile;
+constexpr size_t kPairSmem = sizeof(double) * kPairSmemDoubles + sizeof(long long) * 3 * kTile +
+                             sizeof(int) * 2 * kTile;
 
-__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
+__device__ __forceinline__ void cp_async16(double *dst, const double *src) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
-// dst[kk][r ^ (kk & 15)] <- prof[row(r)][k0 + kk], asynchronously; the XOR makes the
-// transposing store and the strided reads conflict-free.  Rows past the end are zero.
+// dst[r][kk] <- prof[row(r)][k0 + kk], kk < kc (kc = 32 or 8), asynchronously, 16 bytes a time.
+// Rows past the end are zero.
 __device__ __forceinline__ void stage_prof_chunk(double *dst, const double *__restrict__ prof,
-                                                 const long long *rows, int k0) {
-    for (int idx = threadIdx.x; idx < kTile * kKC; idx += kPairThreads) {
-        const int r = idx / kKC;
-        const int kk = idx - r * kKC;
+                                                 const long long *rows, int k0, int kc) {
+    const int pieces = kc >> 1;                   // 16-byte pieces per row
+    const int shift = kc == 32 ? 4 : 2;
+    for (int idx = threadIdx.x; idx < kTile * pieces; idx += kPairThreads) {
+        const int r = idx >> shift;
+        const int p = idx & (pieces - 1);
         const long long row = rows[r];
-        double *d = dst + kk * kTile + (r ^ (kk & 15));
-        if (row >= 0) cp_async8(d, prof + row * MCG_NPROF + k0 + kk);
-        else *d = 0.0;
+        double *d = dst + r * kPitch + 2 * p;
+        if (row >= 0) cp_async16(d, prof + row * MCG_NPROF + k0 + 2 * p);
+        else { d[0] = 0.0; d[1] = 0.0; }
     }
 }
 
@@ -282,52 +313,56 @@ __device__ __forceinline__ void tile_rows(long long *rows, double *norms, const 
 }
 
 // RULE_C: rule-C weights / argmin (label_prop_utils.py:308-345), else raw per-pair outputs.
-// DOT: distance from ||u||^2 + ||v||^2 - 2 u.v (136 FMAs per pair) instead of the
-// difference form (272); used whenever the distance itself is not an output.
 // LOGSUM (S <= 30): the product of the floored Poisson terms is carried as the sum of their
 // floored exponents, prod_s max(e^x_s, 1e-10) = exp(sum_s max(x_s, log 1e-10)): one exp per
 // pair instead of 2 S.  With S <= 30 the sum stays above -691, so neither running product can
 // underflow in the reference either and the two forms agree to ~S ulp.  For S > 30 the
 // reference's products reach the denormal range, where its sequential rounding (and the
 // exact zero that decides prob_product > 0) can only be reproduced by multiplying in order.
-template <bool RULE_C, bool DOT, bool LOGSUM>
+template <bool RULE_C, bool LOGSUM>
 __global__ void __launch_bounds__(kPairThreads, 2)
 pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) double sm[];
-    double *stage = sm;                                   // [2][2][34][64]
+    double *stage = sm;                                   // [2 stages][A, B][64][36]
     double *CA = stage + 4 * kChunkDoubles;
     double *CB = CA + kSampleChunk * 3 * kTile;
     double *NA = CB + kSampleChunk * 3 * kTile;
     double *NB = NA + kTile;                              // [2][64]
     double *ET = NB + 2 * kTile;                          // 16
     double *LT = ET + 16;                                 // 128
-    long long *rowA = reinterpret_cast<long long *>(LT + 128);
+    double *best_w_s = LT + 128;                          // [2][64] cross-warp argmin
+    long long *rowA = reinterpret_cast<long long *>(best_w_s + 2 * kTile);
     long long *rowB = rowA + kTile;                       // [2][64]
+    int *best_i_s = reinterpret_cast<int *>(rowB + 2 * kTile);   // [2][64]
 
     const int tid = threadIdx.x;
-    const int ti = tid >> 4, tj = tid & 15;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = warp >> 1, wc = warp & 1;
+    const int row0 = 16 * wr + g;          // this lane's rows: row0, row0 + 8
+    const int col0 = 32 * wc + 2 * t;      // this lane's columns: col0 + 8 j + {0, 1}
     const long long a0 = static_cast<long long>(blockIdx.x) * kTile;
     const long long n_btiles = (B.n + kTile - 1) / kTile;
     const bool single_chunk = S <= kSampleChunk;
-    constexpr int kChunks = MCG_NPROF / kKC;
+    constexpr int kChunks = (MCG_NPROF + kKC - 1) / kKC;   // 5: four of 32 and one of 8
 
     if (tid < 16) ET[tid] = g_exp_table[tid];
     if (tid < 128) LT[tid] = g_log_table[tid];
-    tile_rows(rowA, NA, A, a0, DOT);
+    tile_rows(rowA, NA, A, a0, true);
     long long bt = blockIdx.y;
-    if (bt < n_btiles) tile_rows(rowB, NB, B, bt * kTile, DOT);
+    if (bt < n_btiles) tile_rows(rowB, NB, B, bt * kTile, true);
     __syncthreads();
     if (single_chunk) load_cov_chunk(CA, A, rowA, S, 0, S);
     if (bt < n_btiles) {   // chunk 0 of the first tile
-        stage_prof_chunk(stage, A.prof, rowA, 0);
-        stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB, 0);
+        stage_prof_chunk(stage, A.prof, rowA, 0, kKC);
+        stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB, 0, kKC);
     }
     cp_async_commit();
 
-    double best_w[4];
-    int best_i[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { best_w[e] = 0.0; best_i[e] = -1; }
+    double best_w[2];
+    int best_i[2];
+    best_w[0] = best_w[1] = 0.0;
+    best_i[0] = best_i[1] = -1;
     bool domain_error = false;
 
     for (int it = 0; bt < n_btiles; bt += gridDim.y, ++it) {
@@ -336,72 +371,82 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
         const long long *rows_b = rowB + cur * kTile;
         const double *norm_b = NB + cur * kTile;
         const long long bt_next = bt + gridDim.y;
+        // 8-column blocks of this warp that hold real B rows (warp-uniform)
+        const long long left = B.n - b0 - 32 * wc;
+        const int njv = left <= 0 ? 0 : (left >= 32 ? 4 : static_cast<int>((left + 7) >> 3));
         // rows of the next tile (its chunk 0 is staged below, during this tile's phase 2)
         if (bt_next < n_btiles) tile_rows(rowB + (cur ^ 1) * kTile, NB + (cur ^ 1) * kTile, B,
-                                          bt_next * kTile, DOT);
+                                          bt_next * kTile, true);
         if (single_chunk) load_cov_chunk(CB, B, rows_b, S, 0, S);
 
-        // ---- squared tetramer distance (matching_utils.py:28-29), k in four chunks -------
-        double acc[4][4];
+        // ---- u.v on the FP64 tensor path (matching_utils.py:28-29), k in five chunks ------
+        double acc[2][4][2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int f = 0; f < 4; ++f) acc[e][f] = 0.0;
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
             if (c + 1 < kChunks) {
                 double *nxt = stage + ((c + 1) & 1) * 2 * kChunkDoubles;
-                stage_prof_chunk(nxt, A.prof, rowA, (c + 1) * kKC);
-                stage_prof_chunk(nxt + kChunkDoubles, B.prof, rows_b, (c + 1) * kKC);
+                const int kc = (c + 1 == kChunks - 1) ? MCG_NPROF - (kChunks - 1) * kKC : kKC;
+                stage_prof_chunk(nxt, A.prof, rowA, (c + 1) * kKC, kc);
+                stage_prof_chunk(nxt + kChunkDoubles, B.prof, rows_b, (c + 1) * kKC, kc);
                 cp_async_commit();
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
             __syncthreads();   // chunk c has landed for everyone
-            const double *Ak = stage + (c & 1) * 2 * kChunkDoubles;
-            const double *Bk = Ak + kChunkDoubles;
+            const double *Ak = stage + (c & 1) * 2 * kChunkDoubles + row0 * kPitch + t;
+            const double *Bk = stage + (c & 1) * 2 * kChunkDoubles + kChunkDoubles +
+                               (32 * wc + g) * kPitch + t;
+            const int ksteps = (c == kChunks - 1) ? (MCG_NPROF - (kChunks - 1) * kKC) / 4 : kKC / 4;
+            if (njv > 0) {
 #pragma unroll 2
-            for (int kk = 0; kk < kKC; ++kk) {
-                const int sw = kk & 15;
-                const double *ar = Ak + kk * kTile + (ti ^ sw);
-                const double *br = Bk + kk * kTile + (tj ^ sw);
-                double a[4], b[4];
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const double a_lo = Ak[4 * ks];
+                    const double a_hi = Ak[8 * kPitch + 4 * ks];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { a[e] = ar[16 * e]; b[e] = br[16 * e]; }
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        if (DOT) {
-                            acc[e][f] = fma(a[e], b[f], acc[e][f]);
-                        } else {
-                            const double d = a[e] - b[f];
-                            acc[e][f] = fma(d, d, acc[e][f]);
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < njv) {
+                            const double b = Bk[8 * j * kPitch + 4 * ks];
+                            dmma(acc[0][j][0], acc[0][j][1], a_lo, b);
+                            dmma(acc[1][j][0], acc[1][j][1], a_hi, b);
                         }
                     }
+                }
             }
             __syncthreads();   // stage c & 1 may be refilled
         }
         if (bt_next < n_btiles) {   // chunk 0 of the next tile flies during phase 2
-            stage_prof_chunk(stage, A.prof, rowA, 0);
-            stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB + (cur ^ 1) * kTile, 0);
+            stage_prof_chunk(stage, A.prof, rowA, 0, kKC);
+            stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB + (cur ^ 1) * kTile, 0, kKC);
         }
         cp_async_commit();
-        if (DOT) {
+        // d^2 = |u|^2 + |v|^2 - 2 u.v, clamped at 0
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const double d2 = fma(-2.0, acc[e][f], NA[ti + 16 * e] + norm_b[tj + 16 * f]);
-                    acc[e][f] = d2 > 0.0 ? d2 : 0.0;
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double d2 = fma(-2.0, acc[i][j][h],
+                                          NA[row0 + 8 * i] + norm_b[col0 + 8 * j + h]);
+                    acc[i][j][h] = d2 > 0.0 ? d2 : 0.0;
                 }
-        }
 
-        // ---- one column of pairs at a time: Poisson products in sample order, epilogue -----
+        // ---- 4 pairs at a time (2 rows x 2 adjacent columns): Poisson terms, epilogue ------
+        // with several sample chunks the loop holds barriers, so every warp runs the trip
+        // count of the fullest warp (wc = 0) and idles through the blocks it does not have
+        const long long left0 = B.n - b0;
+        const int nj_loop = single_chunk ? njv
+                                         : (left0 >= 32 ? 4 : static_cast<int>((left0 + 7) >> 3));
 #pragma unroll 1
-        for (int f = 0; f < 4; ++f) {
-            double p1[4], p2[4];
+        for (int j = 0; j < nj_loop; ++j) {
+            const bool live = j < njv;
+            const int col = col0 + 8 * j;
+            double p1[4], p2[4];   // pair index = 2 * i + h
 #pragma unroll
             for (int e = 0; e < 4; ++e) { p1[e] = LOGSUM ? 0.0 : 1.0; p2[e] = p1[e]; }
             for (int s0 = 0; s0 < S; s0 += kSampleChunk) {
@@ -412,34 +457,46 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                     load_cov_chunk(CB, B, rows_b, S, s0, sc);
                     __syncthreads();
                 }
+                if (!live) continue;
 #pragma unroll 2
                 for (int q = 0; q < sc; ++q) {
-                    const double *ca = CA + q * 3 * kTile + ti;
-                    const double *cb = CB + q * 3 * kTile + tj + 16 * f;
-                    const double bc = cb[0], bl = cb[kTile], bg = cb[2 * kTile];
+                    const double *ca = CA + q * 3 * kTile + row0;
+                    const double2 bc = *reinterpret_cast<const double2 *>(CB + q * 3 * kTile + col);
+                    const double2 bl =
+                        *reinterpret_cast<const double2 *>(CB + (q * 3 + 1) * kTile + col);
+                    const double2 bg =
+                        *reinterpret_cast<const double2 *>(CB + (q * 3 + 2) * kTile + col);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const double ac = ca[16 * e];
-                        const double al = ca[kTile + 16 * e];
-                        const double ag = ca[2 * kTile + 16 * e];
+                    for (int i = 0; i < 2; ++i) {
+                        const double ac = ca[8 * i];
+                        const double al = ca[kTile + 8 * i];
+                        const double ag = ca[2 * kTile + 8 * i];
                         // cov1 = the A row, cov2 = the B row (matching_utils.py:48-54)
                         if (LOGSUM) {
-                            p1[e] += poisson_exponent(ac, ag, bc, bl);
-                            p2[e] += poisson_exponent(bc, bg, ac, al);
+                            p1[2 * i] += poisson_exponent(ac, ag, bc.x, bl.x);
+                            p2[2 * i] += poisson_exponent(bc.x, bg.x, ac, al);
+                            p1[2 * i + 1] += poisson_exponent(ac, ag, bc.y, bl.y);
+                            p2[2 * i + 1] += poisson_exponent(bc.y, bg.y, ac, al);
                         } else {
-                            p1[e] = __dmul_rn(p1[e], poisson_term(ac, ag, bc, bl, ET));
-                            p2[e] = __dmul_rn(p2[e], poisson_term(bc, bg, ac, al, ET));
+                            p1[2 * i] = __dmul_rn(p1[2 * i], poisson_term(ac, ag, bc.x, bl.x, ET));
+                            p2[2 * i] = __dmul_rn(p2[2 * i], poisson_term(bc.x, bg.x, ac, al, ET));
+                            p1[2 * i + 1] =
+                                __dmul_rn(p1[2 * i + 1], poisson_term(ac, ag, bc.y, bl.y, ET));
+                            p2[2 * i + 1] =
+                                __dmul_rn(p2[2 * i + 1], poisson_term(bc.y, bg.y, ac, al, ET));
                         }
                     }
                 }
             }
-            const long long bc = b0 + tj + 16 * f;
+            if (!live) continue;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const long long ar = a0 + ti + 16 * e;
-                // f is a runtime index: pick acc[e][f] without making acc[] addressable
-                const double d2 = f == 0 ? acc[e][0] : f == 1 ? acc[e][1]
-                                : f == 2 ? acc[e][2] : acc[e][3];
+                const int i = e >> 1, h = e & 1;
+                const long long ar = a0 + row0 + 8 * i;
+                const long long bc = b0 + col + h;
+                // j is a runtime index: pick acc[i][j][h] without making acc[] addressable
+                const double d2 = j == 0 ? acc[i][0][h] : j == 1 ? acc[i][1][h]
+                                : j == 2 ? acc[i][2][h] : acc[i][3][h];
                 if (ar >= A.n || bc >= B.n) continue;
                 const double pc = comp_prob_fast(d2, ET);
                 const double pmin = p1[e] < p2[e] ? p1[e] : p2[e];
@@ -458,12 +515,11 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                     const double w = (valid && lp != 0.0) ? lp : MCG_MAX_WEIGHT;
                     if (out.weights) out.weights[o] = w;
                     const int bi = static_cast<int>(bc);
-                    if (best_i[e] < 0 || w < best_w[e] || (w == best_w[e] && bi < best_i[e])) {
-                        best_w[e] = w;
-                        best_i[e] = bi;
+                    if (best_i[i] < 0 || w < best_w[i] || (w == best_w[i] && bi < best_i[i])) {
+                        best_w[i] = w;
+                        best_i[i] = bi;
                     }
                 } else {
-                    if (out.dist) out.dist[o] = sqrt(d2);
                     if (out.pc) out.pc[o] = pc;
                     if (out.pv) out.pv[o] = pv;
                     if (out.lp) out.lp[o] = lp;
@@ -477,26 +533,51 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
     if (domain_error) atomicOr(status, 1);
 
     if (RULE_C) {
-        // first index of the minimum over the 16 column threads of each row
+        // first index of the minimum: over the 4 lanes of a row, then over the two warps
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            double w = best_w[e];
-            int bi = best_i[e];
+        for (int i = 0; i < 2; ++i) {
+            double w = best_w[i];
+            int bi = best_i[i];
 #pragma unroll
-            for (int m = 8; m >= 1; m >>= 1) {
+            for (int m = 2; m >= 1; m >>= 1) {
                 const double ow = __shfl_xor_sync(0xffffffffu, w, m);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
                 if (oi >= 0 && (bi < 0 || ow < w || (ow == w && oi < bi))) { w = ow; bi = oi; }
             }
-            const long long ar = a0 + ti + 16 * e;
-            if (tj == 0 && ar < A.n) {
-                // label_prop_utils.py:342-345: None when the minimum is MAX_WEIGHT
-                const bool none = (bi < 0) || (w == MCG_MAX_WEIGHT);
-                if (out.argmin) out.argmin[ar] = none ? -1 : bi;
-                if (out.wmin) out.wmin[ar] = none ? MCG_MAX_WEIGHT : w;
+            if (t == 0) {
+                best_w_s[wc * kTile + row0 + 8 * i] = w;
+                best_i_s[wc * kTile + row0 + 8 * i] = bi;
             }
         }
+        __syncthreads();
+        if (tid < kTile && a0 + tid < A.n) {
+            double w = best_w_s[tid];
+            int bi = best_i_s[tid];
+            const double ow = best_w_s[kTile + tid];
+            const int oi = best_i_s[kTile + tid];
+            if (oi >= 0 && (bi < 0 || ow < w || (ow == w && oi < bi))) { w = ow; bi = oi; }
+            // label_prop_utils.py:342-345: None when the minimum is MAX_WEIGHT
+            const bool none = (bi < 0) || (w == MCG_MAX_WEIGHT);
+            if (out.argmin) out.argmin[a0 + tid] = none ? -1 : bi;
+            if (out.wmin) out.wmin[a0 + tid] = none ? MCG_MAX_WEIGHT : w;
+        }
     }
+}
+
+// get_tetramer_distance for all pairs in the reference's difference form (diagnostic output of
+// mcg_pair_scores; the scorer itself uses the norm / dot-product form).
+__global__ void pair_distance_kernel(ScoreSide A, ScoreSide B, double *__restrict__ dist) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= A.n * B.n) return;
+    const long long qa = i / B.n, qb = i - qa * B.n;
+    const double *u = A.prof + (A.index ? A.index[qa] : qa) * MCG_NPROF;
+    const double *v = B.prof + (B.index ? B.index[qb] : qb) * MCG_NPROF;
+    double acc = 0.0;
+    for (int k = 0; k < MCG_NPROF; ++k) {
+        const double d = u[k] - v[k];
+        acc = fma(d, d, acc);
+    }
+    dist[i] = sqrt(acc);
 }
 
 // Rules A / B over a raw lp matrix [nq, nm]: members of bin b are the columns
@@ -608,13 +689,9 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 
 // ---- launchers -------------------------------------------------------------------------------
 typedef void (*pair_fn)(ScoreSide, ScoreSide, int, ScoreOut, int32_t *);
-static pair_fn pair_variant(bool rule_c, bool dot, bool logsum) {
-    if (rule_c) {
-        if (dot) return logsum ? pair_kernel<true, true, true> : pair_kernel<true, true, false>;
-        return logsum ? pair_kernel<true, false, true> : pair_kernel<true, false, false>;
-    }
-    if (dot) return logsum ? pair_kernel<false, true, true> : pair_kernel<false, true, false>;
-    return logsum ? pair_kernel<false, false, true> : pair_kernel<false, false, false>;
+static pair_fn pair_variant(bool rule_c, bool logsum) {
+    if (rule_c) return logsum ? pair_kernel<true, true> : pair_kernel<true, false>;
+    return logsum ? pair_kernel<false, true> : pair_kernel<false, false>;
 }
 
 static int ensure_gauss(mcg_ctx *ctx) {
@@ -662,8 +739,8 @@ static int ensure_gauss(mcg_ctx *ctx) {
     MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_math, &m, sizeof m, 0, cudaMemcpyHostToDevice,
                                           ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int v = 0; v < 8; ++v) MCG_CUDA(ctx, cudaFuncSetAttribute(
-        pair_variant(v & 4, v & 2, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    for (int v = 0; v < 4; ++v) MCG_CUDA(ctx, cudaFuncSetAttribute(
+        pair_variant(v & 2, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
         static_cast<int>(kPairSmem)));
     if (ctx->device < 64) ready[ctx->device] = true;
     return MCG_OK;
@@ -683,7 +760,8 @@ int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam,
 
 int mcg_k_row_norms(mcg_ctx *ctx, const double *d_prof, int64_t rows, double *d_norm) {
     if (rows == 0) return MCG_OK;
-    row_norms_kernel<<<blocks_for(rows * 32, 256), 256, 0, ctx->stream>>>(d_prof, rows, d_norm);
+    row_norms_kernel<<<blocks_for(((rows + 7) / 8) * 32, 256), 256, 0, ctx->stream>>>(d_prof, rows,
+                                                                                      d_norm);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }
@@ -697,10 +775,11 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
     const long long b_tiles = (b.n + kTile - 1) / kTile;
     if (a_tiles > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many query rows");
     dim3 grid(static_cast<unsigned>(a_tiles), 1, 1);
-    // the dot-product form needs the squared norms of both sides and is used whenever the
-    // distance itself is not reported
-    const bool dot = out.dist == nullptr && a.norm != nullptr && b.norm != nullptr;
     const bool logsum = n_samples <= 30;
+    if (out.dist) {
+        pair_distance_kernel<<<blocks_for(a.n * b.n, 128), 128, 0, ctx->stream>>>(a, b, out.dist);
+        MCG_KERNEL_CHECK(ctx);
+    }
     if (!rule_c) {
         // few query tiles: spread the B tiles over grid.y to fill the SMs
         long long gy = (2LL * ctx->sm_count + a_tiles - 1) / a_tiles;
@@ -709,7 +788,7 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
         if (gy > 65535) gy = 65535;
         grid.y = static_cast<unsigned>(gy);
     }
-    pair_variant(rule_c, dot, logsum)<<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
+    pair_variant(rule_c, logsum)<<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
         a, b, n_samples, out, d_status);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
