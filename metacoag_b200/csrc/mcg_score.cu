@@ -116,6 +116,7 @@ struct MathConst {
     double l7, l6, l5, l4, l3;                        // 1/7, -1/6, 1/5, -1/4, 1/3
     double log_floor;                                 // log(1e-10), matching_utils.py:14
     double inv_two_var_intra, inv_denom_intra, inv_two_var_inter, inv_denom_inter, inv_ln10;
+    double log_inv_denom_intra;                       // -log(sd_intra * sqrt(2 pi))
 };
 __constant__ MathConst c_math;
 
@@ -186,6 +187,30 @@ __device__ __forceinline__ double comp_prob_fast(double d2, const double *__rest
 }
 
 
+__device__ __noinline__ double exp_slow(double x) { return exp(x); }
+
+// log(prob_comp), or NaN when prob_comp is exactly 0 (an underflowed intra Gaussian,
+// d >~ 0.21).  Fast path: log gi is its exponent minus log(sd sqrt(2 pi)), so one table log of
+// gi + ge replaces the division and the log of the quotient.
+__device__ __forceinline__ double log_comp_prob(double d2, const double *__restrict__ etab,
+                                                const double *__restrict__ ltab,
+                                                bool *domain_error) {
+    const double d = sqrt(d2);
+    const double dx = __dsub_rn(d, c_gauss.mu_inter);
+    const double ai = -d2 * c_math.inv_two_var_intra;
+    const double ae = -(dx * dx) * c_math.inv_two_var_inter;
+    if (ai < -746.0 && ae >= -700.0) return __longlong_as_double(0x7ff8000000000000LL);
+    if (ai < -700.0 || ae < -700.0 || !(ai <= 0.0)) {
+        const double pc = comp_prob_dev(d);
+        if (pc != pc) *domain_error = true;
+        if (!(pc > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+        return log_core(pc, ltab);
+    }
+    const double gi = exp_core(ai, etab) * c_math.inv_denom_intra;
+    const double ge = exp_core(ae, etab) * c_math.inv_denom_inter;
+    return (ai + c_math.log_inv_denom_intra) - log_core(gi + ge, ltab);
+}
+
 // ---- coverage terms --------------------------------------------------------------------
 // status bit 2: a coverage value is NaN or infinite (the fast exp path assumes finite inputs).
 __global__ void cov_terms_kernel(double *__restrict__ cov, double *__restrict__ logc,
@@ -244,17 +269,22 @@ __global__ void row_norms_kernel(const double *__restrict__ prof, long long rows
 //             Poisson terms over the samples for 4 pairs at a time, then the epilogue.
 //
 // 112 KB of shared memory per CTA and <= 128 registers: two CTAs share an SM.
-constexpr int kKC = 32;                       // k-chunk (8 DMMA k-steps); 136 = 4 * 32 + 8
-constexpr int kPitch = kKC + 4;               // pitch = 4 mod 16 doubles: conflict-free fragments
+constexpr int kKC = 24;                       // k-chunk (6 DMMA k-steps); 136 = 5 * 24 + 16
+constexpr int kPitch = kKC + 4;               // pitch = 12 mod 16 doubles: conflict-free fragments
 constexpr int kChunkDoubles = kTile * kPitch; // one side of one stage
-constexpr int kPairSmemDoubles = 4 * kChunkDoubles + 2 * kSampleChunk * 3 * kTile + 3 * kTile +
-                                 16 + 128 + 2 * kTile;
+constexpr int kCovDoubles = kSampleChunk * 3 * kTile;   // one side's coverage terms
+constexpr int kPairSmemDoubles = 4 * kChunkDoubles + 3 * kCovDoubles + 3 * kTile + 16 + 128 +
+                                 2 * kTile;
 constexpr size_t kPairSmem = sizeof(double) * kPairSmemDoubles + sizeof(long long) * 3 * kTile +
                              sizeof(int) * 2 * kTile;
 
 __device__ __forceinline__ void cp_async16(double *dst, const double *src) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
@@ -270,10 +300,9 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 __device__ __forceinline__ void stage_prof_chunk(double *dst, const double *__restrict__ prof,
                                                  const long long *rows, int k0, int kc) {
     const int pieces = kc >> 1;                   // 16-byte pieces per row
-    const int shift = kc == 32 ? 4 : 2;
     for (int idx = threadIdx.x; idx < kTile * pieces; idx += kPairThreads) {
-        const int r = idx >> shift;
-        const int p = idx & (pieces - 1);
+        const int r = idx / pieces;
+        const int p = idx - r * pieces;
         const long long row = rows[r];
         double *d = dst + r * kPitch + 2 * p;
         if (row >= 0) cp_async16(d, prof + row * MCG_NPROF + k0 + 2 * p);
@@ -301,6 +330,25 @@ __device__ __forceinline__ void load_cov_chunk(double *dst, const ScoreSide &s,
     }
 }
 
+// The same for the B side of the *next* tile, without stalling: 8-byte cp.async.
+__device__ __forceinline__ void stage_cov_async(double *dst, const ScoreSide &s,
+                                                const long long *rows, int S) {
+    for (int idx = threadIdx.x; idx < kTile * S; idx += kPairThreads) {
+        const int r = idx / S;
+        const int q = idx - r * S;
+        const long long row = rows[r];
+        double *d = dst + q * 3 * kTile + r;
+        if (row >= 0) {
+            const long long off = row * S + q;
+            cp_async8(d, s.cov + off);
+            cp_async8(d + kTile, s.logc + off);
+            cp_async8(d + 2 * kTile, s.lgam + off);
+        } else {
+            d[0] = 1.0; d[kTile] = 0.0; d[2 * kTile] = 0.0;
+        }
+    }
+}
+
 __device__ __forceinline__ void tile_rows(long long *rows, double *norms, const ScoreSide &s,
                                           long long r0, bool want_norm) {
     const int tid = threadIdx.x;
@@ -325,8 +373,8 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
     extern __shared__ __align__(16) double sm[];
     double *stage = sm;                                   // [2 stages][A, B][64][36]
     double *CA = stage + 4 * kChunkDoubles;
-    double *CB = CA + kSampleChunk * 3 * kTile;
-    double *NA = CB + kSampleChunk * 3 * kTile;
+    double *CB2 = CA + kCovDoubles;                       // [2] B-side terms, double-buffered
+    double *NA = CB2 + 2 * kCovDoubles;
     double *NB = NA + kTile;                              // [2][64]
     double *ET = NB + 2 * kTile;                          // 16
     double *LT = ET + 16;                                 // 128
@@ -344,7 +392,7 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
     const long long a0 = static_cast<long long>(blockIdx.x) * kTile;
     const long long n_btiles = (B.n + kTile - 1) / kTile;
     const bool single_chunk = S <= kSampleChunk;
-    constexpr int kChunks = (MCG_NPROF + kKC - 1) / kKC;   // 5: four of 32 and one of 8
+    constexpr int kChunks = (MCG_NPROF + kKC - 1) / kKC;   // 6: five of 24 and one of 16
 
     if (tid < 16) ET[tid] = g_exp_table[tid];
     if (tid < 128) LT[tid] = g_log_table[tid];
@@ -353,9 +401,10 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
     if (bt < n_btiles) tile_rows(rowB, NB, B, bt * kTile, true);
     __syncthreads();
     if (single_chunk) load_cov_chunk(CA, A, rowA, S, 0, S);
-    if (bt < n_btiles) {   // chunk 0 of the first tile
+    if (bt < n_btiles) {   // chunk 0 and the coverage terms of the first tile
         stage_prof_chunk(stage, A.prof, rowA, 0, kKC);
         stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB, 0, kKC);
+        if (single_chunk) stage_cov_async(CB2, B, rowB, S);
     }
     cp_async_commit();
 
@@ -377,7 +426,7 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
         // rows of the next tile (its chunk 0 is staged below, during this tile's phase 2)
         if (bt_next < n_btiles) tile_rows(rowB + (cur ^ 1) * kTile, NB + (cur ^ 1) * kTile, B,
                                           bt_next * kTile, true);
-        if (single_chunk) load_cov_chunk(CB, B, rows_b, S, 0, S);
+        double *CB = CB2 + (single_chunk ? cur : 0) * kCovDoubles;
 
         // ---- u.v on the FP64 tensor path (matching_utils.py:28-29), k in five chunks ------
         double acc[2][4][2];
@@ -422,6 +471,8 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
         if (bt_next < n_btiles) {   // chunk 0 of the next tile flies during phase 2
             stage_prof_chunk(stage, A.prof, rowA, 0, kKC);
             stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB + (cur ^ 1) * kTile, 0, kKC);
+            if (single_chunk)
+                stage_cov_async(CB2 + (cur ^ 1) * kCovDoubles, B, rowB + (cur ^ 1) * kTile, S);
         }
         cp_async_commit();
         // d^2 = |u|^2 + |v|^2 - 2 u.v, clamped at 0
@@ -498,15 +549,31 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                 const double d2 = j == 0 ? acc[i][0][h] : j == 1 ? acc[i][1][h]
                                 : j == 2 ? acc[i][2][h] : acc[i][3][h];
                 if (ar >= A.n || bc >= B.n) continue;
-                const double pc = comp_prob_fast(d2, ET);
-                const double pmin = p1[e] < p2[e] ? p1[e] : p2[e];
-                const double pv = LOGSUM ? exp_core(pmin, ET) : pmin;
-                if (pc != pc) domain_error = true;
-                const bool valid = __dmul_rn(pc, pv) > 0.0;
-                double lp = MCG_MAX_WEIGHT;
-                if (valid) {   // -(log(pc, 10) + log(pv, 10))
-                    const double log_pv = LOGSUM ? pmin : log_core(pv, LT);
-                    lp = -(log_core(pc, LT) + log_pv) * c_math.inv_ln10;
+                const double pmin = p1[e] < p2[e] ? p1[e] : p2[e];   // log or value of prob_cov
+                double lp = MCG_MAX_WEIGHT, pc = 0.0, pv = 0.0;
+                bool valid = false;
+                if (RULE_C && LOGSUM) {
+                    // only -(log10 pc + log10 pv) is needed: log pc = ai - log(sd sqrt(2 pi)) -
+                    // log(gi + ge) avoids the division, log pv is the exponent sum itself
+                    const double log_pc = log_comp_prob(d2, ET, LT, &domain_error);
+                    if (log_pc == log_pc) {   // NaN = prob_comp is exactly 0
+                        const double tsum = log_pc + pmin;
+                        // prob_comp * prob_cov > 0.0 in double arithmetic: certain above
+                        // e^-744, impossible below e^-746 (2^-1075 = e^-745.13)
+                        if (tsum > -744.0) valid = true;
+                        else if (tsum >= -746.0)
+                            valid = __dmul_rn(exp_slow(log_pc), exp_slow(pmin)) > 0.0;
+                        if (valid) lp = -tsum * c_math.inv_ln10;
+                    }
+                } else {
+                    pc = comp_prob_fast(d2, ET);
+                    pv = LOGSUM ? exp_core(pmin, ET) : pmin;
+                    if (pc != pc) domain_error = true;
+                    valid = __dmul_rn(pc, pv) > 0.0;
+                    if (valid) {   // -(log(pc, 10) + log(pv, 10))
+                        const double log_pv = LOGSUM ? pmin : log_core(pv, LT);
+                        lp = -(log_core(pc, LT) + log_pv) * c_math.inv_ln10;
+                    }
                 }
                 const long long o = ar * B.n + bc;
                 if (RULE_C) {
@@ -736,6 +803,7 @@ static int ensure_gauss(mcg_ctx *ctx) {
     m.inv_two_var_inter = 1.0 / g.two_var_inter;
     m.inv_denom_inter = 1.0 / g.denom_inter;
     m.inv_ln10 = 1.0 / g.ln10;
+    m.log_inv_denom_intra = -log(g.denom_intra);
     MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_math, &m, sizeof m, 0, cudaMemcpyHostToDevice,
                                           ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
