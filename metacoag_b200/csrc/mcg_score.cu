@@ -295,18 +295,17 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// dst[r][kk] <- prof[row(r)][k0 + kk], kk < kc (kc = 32 or 8), asynchronously, 16 bytes a time.
-// Rows past the end are zero.
+// dst[r][kk] <- prof[row(r)][k0 + kk], kk < kc, asynchronously, 16 bytes a time: four
+// threads per row, thread (r, p0) takes pieces p0, p0 + 4, ...  Rows past the end are zero.
 __device__ __forceinline__ void stage_prof_chunk(double *dst, const double *__restrict__ prof,
                                                  const long long *rows, int k0, int kc) {
-    const int pieces = kc >> 1;                   // 16-byte pieces per row
-    for (int idx = threadIdx.x; idx < kTile * pieces; idx += kPairThreads) {
-        const int r = idx / pieces;
-        const int p = idx - r * pieces;
-        const long long row = rows[r];
-        double *d = dst + r * kPitch + 2 * p;
-        if (row >= 0) cp_async16(d, prof + row * MCG_NPROF + k0 + 2 * p);
-        else { d[0] = 0.0; d[1] = 0.0; }
+    const int r = threadIdx.x >> 2;
+    const long long row = rows[r];
+    double *d = dst + r * kPitch;
+    const double *src = prof + row * MCG_NPROF + k0;
+    for (int kk = 2 * (threadIdx.x & 3); kk < kc; kk += 8) {
+        if (row >= 0) cp_async16(d + kk, src + kk);
+        else { d[kk] = 0.0; d[kk + 1] = 0.0; }
     }
 }
 
@@ -330,13 +329,13 @@ __device__ __forceinline__ void load_cov_chunk(double *dst, const ScoreSide &s,
     }
 }
 
-// The same for the B side of the *next* tile, without stalling: 8-byte cp.async.
+// The same for the B side of the *next* tile, without stalling: 8-byte cp.async, four
+// threads per row.
 __device__ __forceinline__ void stage_cov_async(double *dst, const ScoreSide &s,
                                                 const long long *rows, int S) {
-    for (int idx = threadIdx.x; idx < kTile * S; idx += kPairThreads) {
-        const int r = idx / S;
-        const int q = idx - r * S;
-        const long long row = rows[r];
+    const int r = threadIdx.x >> 2;
+    const long long row = rows[r];
+    for (int q = threadIdx.x & 3; q < S; q += 4) {
         double *d = dst + q * 3 * kTile + r;
         if (row >= 0) {
             const long long off = row * S + q;
