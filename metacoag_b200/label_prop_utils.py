@@ -1,0 +1,333 @@
+"""Drop-in for ``metacoag_utils/label_prop_utils.py`` (MetaCoAG v1.1.5) on the B200 path.
+
+The candidate search (bounded BFS to labelled contigs with the reference's depth bookkeeping)
+and the rule-B / rule-C scoring run in libmcg_b200.so; the priority-queue loop and the
+marker-gene rules stay on the host, in the reference's order.  Citations are
+``label_prop_utils.py:line`` of the reference.
+"""
+import heapq
+import logging
+import sys
+
+import numpy as np
+
+from . import _backend
+from ._lib import RULE_B
+
+MAX_WEIGHT = sys.float_info.max
+
+logger = logging.getLogger("MetaCoaAG 1.1.5")
+
+
+class DataWrap:
+    """Heap entry ordered by (depth, score) of its 5-tuple (:16-21)."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def __lt__(self, other):
+        return (self.data[3], self.data[4]) < (other.data[3], other.data[4])
+
+
+# ---- assembly graph as CSR -----------------------------------------------------------------
+class _GraphCache:
+    """CSR copy of the duck-typed assembly graph (``neighbors(v, mode="ALL")``), built once
+    per graph object; neighbour order is kept as the graph reports it."""
+
+    def __init__(self):
+        self.key = None
+        self.indptr = self.indices = None
+
+    def get(self, assembly_graph, n_vertices):
+        key = (id(assembly_graph), n_vertices)
+        if key != self.key:
+            indptr = np.zeros(n_vertices + 1, dtype=np.int64)
+            chunks = []
+            for v in range(n_vertices):
+                nb = assembly_graph.neighbors(v, mode="ALL")
+                indptr[v + 1] = indptr[v] + len(nb)
+                chunks.append(np.asarray(nb, dtype=np.int32))
+            self.indices = (np.concatenate(chunks) if chunks and indptr[-1] > 0
+                            else np.zeros(0, dtype=np.int32))
+            self.indptr = indptr
+            self.key = key
+        return self.indptr, self.indices
+
+
+_graphs = _GraphCache()
+
+
+def _vertex_count(assembly_graph, *dicts):
+    if hasattr(assembly_graph, "vcount"):
+        return int(assembly_graph.vcount())
+    n = 0
+    for d in dicts:
+        if len(d):
+            n = max(n, max(d) + 1)
+    return n
+
+
+class _SeedScores:
+    """Rule-B score of (node, bin): mean -log10 score against the first
+    ``smg_bin_counts[bin]`` members of the bin (:54-86).  Those members never change during a
+    stage, so the score is computed once per node, for all bins in one launch."""
+
+    def __init__(self, bins, smg_bin_counts, profiles, coverages):
+        self.order = list(bins)
+        self.col = {b: i for i, b in enumerate(self.order)}
+        self.members, self.seg = _backend.csr_bins(bins, self.order, smg_bin_counts)
+        self.profiles, self.coverages = profiles, coverages
+        self.rows = {}
+
+    def ensure(self, nodes):
+        todo = [n for n in dict.fromkeys(int(x) for x in nodes) if n not in self.rows]
+        if todo:
+            w = _backend.backend().score_members(self.profiles, self.coverages,
+                                                 np.asarray(todo, dtype=np.int64), self.members,
+                                                 self.seg, RULE_B)
+            for i, n in enumerate(todo):
+                self.rows[n] = w[i]
+
+    def get(self, node, bin_):
+        return float(self.rows[node][self.col[bin_]])
+
+
+def _bfs_hits(nodes, threshold, bin_of_contig, assembly_graph, n_vertices):
+    """For every start node the (labelled node, bin, depth) triples of run_bfs_long, in the
+    reference's pop order."""
+    indptr, indices = _graphs.get(assembly_graph, n_vertices)
+    labels = np.full(n_vertices, -1, dtype=np.int32)
+    for contig, b in bin_of_contig.items():
+        labels[contig] = b
+    starts = np.asarray(list(nodes), dtype=np.int64)
+    node, bin_, depth, n_hits = _backend.backend().bfs_candidates(indptr, indices, labels, starts,
+                                                                  threshold)
+    return [[(int(node[i, h]), int(bin_[i, h]), int(depth[i, h])) for h in range(int(n_hits[i]))]
+            for i in range(starts.shape[0])]
+
+
+def _candidates(nodes, threshold, bin_of_contig, scores, assembly_graph, n_vertices):
+    """``[set of (node, labelled, bin, depth, score)]`` per node, the sets built by inserting
+    the hits in pop order like the reference does (:88-90)."""
+    nodes = list(nodes)
+    hits = _bfs_hits(nodes, threshold, bin_of_contig, assembly_graph, n_vertices)
+    scores.ensure(n for n, h in zip(nodes, hits) if h)
+    out = []
+    for n, node_hits in zip(nodes, hits):
+        found = set()
+        for labelled, b, d in node_hits:
+            found.add((n, labelled, b, d, scores.get(n, b)))
+        out.append(found)
+    return out
+
+
+def run_bfs_long(node, threhold, binned_contigs, bin_of_contig, bins, smg_bin_counts,
+                 assembly_graph, normalized_tetramer_profiles, coverages):
+    """Bounded BFS from ``node`` to labelled contigs (:24-100): a set of
+    ``(node, labelled node, bin, depth, score)``."""
+    n_vertices = _vertex_count(assembly_graph, bin_of_contig, normalized_tetramer_profiles,
+                               {node: 0})
+    scores = _SeedScores(bins, smg_bin_counts, normalized_tetramer_profiles, coverages)
+    return _candidates([node], threhold, bin_of_contig, scores, assembly_graph, n_vertices)[0]
+
+
+def run_bfs_short(node, threhold, binned_contigs, bin_of_contig, assembly_graph, coverages):
+    """Never called by the pipeline; kept for the interface.
+    Same traversal, score = Euclidean distance of the coverage vectors (:103-141)."""
+    n_vertices = _vertex_count(assembly_graph, bin_of_contig, {node: 0})
+    hits = _bfs_hits([node], threhold, bin_of_contig, assembly_graph, n_vertices)[0]
+    found = set()
+    for labelled, b, d in hits:
+        dist = float(_backend.backend().tetramer_distance(
+            np.asarray(coverages[labelled], dtype=np.float64),
+            np.asarray(coverages[node], dtype=np.float64))[0])
+        found.add((node, labelled, b, d, dist))
+    return found
+
+
+def getClosestLongVertices(graph, node, binned_contigs, contig_lengths, min_length):
+    """Level-order search from ``node``: the long unbinned contigs of the first level that has
+    any (:144-172).  Levels are deduplicated and never revisit a vertex."""
+    binned = binned_contigs if isinstance(binned_contigs, (set, frozenset, dict)) \
+        else set(binned_contigs)
+    visited = {node}
+    level = list(graph.neighbors(node, mode="ALL"))
+    while level:
+        visited.update(level)
+        unlabelled = [n for n in level if contig_lengths[n] >= min_length and n not in binned]
+        if unlabelled:
+            return unlabelled
+        merged = []
+        for n in level:
+            merged = list(set(merged + list(graph.neighbors(n, mode="ALL"))))
+        level = [n for n in merged if n not in visited]
+    return []
+
+
+def _closest_long(graph, node, bin_of_contig, contig_lengths, min_length):
+    return [x for x in getClosestLongVertices(graph, node, bin_of_contig, contig_lengths,
+                                              min_length)
+            if contig_lengths[x] >= min_length]
+
+
+def _propagate(bin_of_contig, bins, contig_markers, bin_markers, binned_contigs_with_markers,
+               smg_bin_counts, seeds, contig_lengths, min_length, assembly_graph,
+               normalized_tetramer_profiles, coverages, depth, accept):
+    """The shared heap loop of label_prop (:196-305) and final_label_prop (:419-511)."""
+    n_vertices = _vertex_count(assembly_graph, contig_lengths, bin_of_contig)
+    scores = _SeedScores(bins, smg_bin_counts, normalized_tetramer_profiles, coverages)
+
+    contigs_to_bin = set()
+    for contig in seeds:
+        contigs_to_bin.update(_closest_long(assembly_graph, contig, bin_of_contig, contig_lengths,
+                                            min_length))
+
+    heap = []
+    for found in _candidates(contigs_to_bin, depth, bin_of_contig, scores, assembly_graph,
+                             n_vertices):
+        for data in list(found):
+            heapq.heappush(heap, DataWrap(data))
+
+    while heap:
+        to_bin, binned, bin_, dist, score = heapq.heappop(heap).data
+
+        has_mg = False
+        common_mgs = set()
+        if to_bin in contig_markers:
+            has_mg = True
+            common_mgs = set(bin_markers[bin_]).intersection(set(contig_markers[to_bin]))
+            if binned in contig_markers and dist == 1:
+                neighbour_common = set(contig_markers[binned]).intersection(
+                    set(contig_markers[to_bin]))
+                if neighbour_common == common_mgs:
+                    common_mgs = set()
+
+        if not accept(to_bin, score, dist, common_mgs):
+            continue
+
+        bins[bin_].append(to_bin)
+        bin_of_contig[to_bin] = bin_
+        if has_mg:
+            binned_contigs_with_markers.append(to_bin)
+            bin_markers[bin_] = list(set(bin_markers[bin_] + contig_markers[to_bin]))
+
+        # the contigs around the new member get fresh candidates
+        around = set(_closest_long(assembly_graph, to_bin, bin_of_contig, contig_lengths,
+                                   min_length))
+        heap = [x for x in heap if x.data[0] not in around]
+        heapq.heapify(heap)
+        for found in _candidates(around, depth, bin_of_contig, scores, assembly_graph,
+                                 n_vertices):
+            for data in list(found):
+                heapq.heappush(heap, DataWrap(data))
+
+    return bins, bin_of_contig, bin_markers, binned_contigs_with_markers
+
+
+def label_prop(bin_of_contig, bins, contig_markers, bin_markers, binned_contigs_with_markers,
+               smg_bin_counts, non_isolated, contig_lengths, min_length, assembly_graph,
+               normalized_tetramer_profiles, coverages, depth, weight):
+    """Label propagation from the binned long contigs listed in ``non_isolated`` (:175-305).
+    A candidate is accepted when it is still unbinned, scores below ``weight``, lies within
+    ``depth`` and shares no marker gene with the bin (or one, if longer than 100 kb)."""
+    seeds = [c for c in bin_of_contig
+             if c in non_isolated and contig_lengths[c] >= min_length]
+
+    def accept(to_bin, score, dist, common_mgs):
+        if to_bin in bin_of_contig or not (score < weight and dist <= depth):
+            return False
+        return len(common_mgs) == 0 or (len(common_mgs) <= 1 and contig_lengths[to_bin] > 100000)
+
+    return _propagate(bin_of_contig, bins, contig_markers, bin_markers,
+                      binned_contigs_with_markers, smg_bin_counts, seeds, contig_lengths,
+                      min_length, assembly_graph, normalized_tetramer_profiles, coverages, depth,
+                      accept)
+
+
+# ---- rule C: contig against bin centroids ------------------------------------------------------
+class _CentroidCache:
+    """assign_long is called once per contig, from several threads (metacoag:959-999).  The
+    first call of a stage scores every staged long contig against the centroids in one
+    launch; the other calls are lookups."""
+
+    def __init__(self):
+        self.key = None
+        self.result = {}
+        import threading
+        self.lock = threading.Lock()
+
+    def lookup(self, contigid, coverages, profiles, bin_tetramer_profiles,
+               bin_coverage_profiles):
+        key = (id(coverages), id(profiles), id(bin_tetramer_profiles),
+               id(bin_coverage_profiles), len(bin_tetramer_profiles), len(profiles))
+        with self.lock:
+            if key != self.key or contigid not in self.result:
+                order = list(bin_tetramer_profiles)
+                cen_prof = np.stack([np.asarray(bin_tetramer_profiles[b], dtype=np.float64)
+                                     for b in order])
+                cen_cov = np.stack([np.asarray(bin_coverage_profiles[b], dtype=np.float64)
+                                    for b in order])
+                queries = sorted(c for c in profiles if c in coverages)
+                if contigid not in profiles:
+                    raise KeyError(contigid)
+                arg, w = _backend.backend().score_centroids(
+                    profiles, coverages, np.asarray(queries, dtype=np.int64), cen_prof, cen_cov)
+                self.result = {c: (int(a), float(x)) for c, a, x in zip(queries, arg, w)}
+                self.key = key
+            return self.result[contigid]
+
+
+_centroids = _CentroidCache()
+
+
+def assign_long(contigid, coverages, normalized_tetramer_profiles, bin_tetramer_profiles,
+                bin_coverage_profiles):
+    """``(contigid, index of the best bin, weight)`` or ``None`` when no bin scores (:308-345).
+    The index is the position in ``bin_tetramer_profiles``' iteration order, first minimum."""
+    best, weight = _centroids.lookup(contigid, coverages, normalized_tetramer_profiles,
+                                     bin_tetramer_profiles, bin_coverage_profiles)
+    if best < 0:
+        return None
+    return contigid, best, weight
+
+
+def assign_to_bins(put_to_bins, bins, bin_of_contig, bin_markers, binned_contigs_with_markers,
+                   contig_markers, contig_lengths):
+    """Applies assign_long's results in the given order with the marker-gene rule (:348-391)."""
+    for contig, contig_bin, bin_weight in put_to_bins:
+        if contig_bin is None:
+            continue
+        has_mg = contig in contig_markers
+        common_mgs = []
+        if has_mg:
+            common_mgs = list(set(bin_markers[contig_bin]).intersection(
+                set(contig_markers[contig])))
+        can_bin = False
+        if contig not in bin_of_contig and bin_weight != MAX_WEIGHT:
+            if len(common_mgs) == 0 or (len(common_mgs) <= 1 and contig_lengths[contig] > 100000):
+                can_bin = True
+        if can_bin:
+            bins[contig_bin].append(contig)
+            bin_of_contig[contig] = contig_bin
+            if has_mg:
+                binned_contigs_with_markers.append(contig)
+                bin_markers[contig_bin] = list(set(bin_markers[contig_bin]
+                                                   + contig_markers[contig]))
+    return bins, bin_of_contig, bin_markers, binned_contigs_with_markers
+
+
+def final_label_prop(bin_of_contig, bins, contig_markers, bin_markers,
+                     binned_contigs_with_markers, smg_bin_counts, contig_lengths, min_length,
+                     assembly_graph, normalized_tetramer_profiles, coverages, depth, weight):
+    """Last propagation pass from every binned long contig (:394-513): a candidate is accepted
+    when it is still unbinned and its score is not ``weight`` (MAX_WEIGHT in the pipeline);
+    the marker-gene sets are computed but do not gate this pass."""
+    seeds = [c for c in bin_of_contig if contig_lengths[c] >= min_length]
+
+    def accept(to_bin, score, dist, common_mgs):
+        return to_bin not in bin_of_contig and score != weight
+
+    return _propagate(bin_of_contig, bins, contig_markers, bin_markers,
+                      binned_contigs_with_markers, smg_bin_counts, seeds, contig_lengths,
+                      min_length, assembly_graph, normalized_tetramer_profiles, coverages, depth,
+                      accept)
