@@ -71,6 +71,15 @@ def workload_tables(seed, n_contigs, n_samples, n_bins):
                 seg=np.array(seg, np.int64))
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -191,7 +200,7 @@ def run_reference(args, rank, world):
     value = sample / dt
     desc = "first %d contigs (%.1f Mbp) x %d bins per step, %d host threads" % (
         sample, offsets[sample] / 1e6, N_BINS, cores)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "contigs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -202,10 +211,16 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "contigs/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def main():
+    # libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line
+    # on stdout, so everything else goes to stderr and the line is written to the saved fd
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -394,7 +409,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline(blob, offsets, coverage, cen_prof, cen_cov,
                                             args.cpu_budget)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
