@@ -591,6 +591,7 @@ static ScoreSide contig_side(mcg_ctx *ctx, const int64_t *d_index, int64_t n) {
     s.lgam = ctx->lgam.as<double>();
     s.norm = ctx->prof_norm.as<double>();
     s.index = d_index;
+    s.first = 0;
     s.n = n;
     return s;
 }
@@ -603,6 +604,7 @@ static ScoreSide centroid_side(mcg_ctx *ctx) {
     s.lgam = ctx->cen_lgam.as<double>();
     s.norm = ctx->cen_norm.as<double>();
     s.index = nullptr;
+    s.first = 0;
     s.n = ctx->n_bins;
     return s;
 }

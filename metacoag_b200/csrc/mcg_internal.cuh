@@ -148,6 +148,7 @@ struct ScoreSide {
     const double *lgam;   // [rows,S]
     const double *norm;   // [rows] squared L2 norm of each profile row
     const int64_t *index; // gather index or nullptr (identity)
+    int64_t first;        // offset into index (or first row when index is nullptr)
     int64_t n;            // rows addressed on this side
 };
 struct ScoreOut {

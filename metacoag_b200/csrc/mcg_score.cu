@@ -117,6 +117,7 @@ struct MathConst {
     double log_floor;                                 // log(1e-10), matching_utils.py:14
     double inv_two_var_intra, inv_denom_intra, inv_two_var_inter, inv_denom_inter, inv_ln10;
     double log_inv_denom_intra;                       // -log(sd_intra * sqrt(2 pi))
+    double sd_ratio;                                  // sd_intra / sd_inter
 };
 __constant__ MathConst c_math;
 
@@ -138,13 +139,42 @@ __device__ __forceinline__ double exp_core(double x, const double *__restrict__ 
     return __hiloint2double(hi, __double2loint(res));
 }
 
+// exp(x) for x in (-746, -690]: the value is scaled up by 2^1000 (an exponent-field add, exact)
+// and one multiplication by 2^-1000 then rounds it onto the denormal grid, the single rounding
+// a correctly rounded exp() performs there.
+__device__ __forceinline__ double exp_gradual(double x, const double *__restrict__ table) {
+    const double kd = fma(x, c_math.inv_ln2_16, c_math.magic);
+    const int ki = __double2loint(kd);
+    const double kf = kd - c_math.magic;
+    double r = fma(kf, c_math.ln2_16_hi, x);
+    r = fma(kf, c_math.ln2_16_lo, r);
+    double q = fma(r, c_math.e7, c_math.e6);
+    q = fma(q, r, c_math.e5);
+    q = fma(q, r, c_math.e4);
+    q = fma(q, r, c_math.e3);
+    q = fma(q, r, 0.5);
+    const double em1 = fma(q, r * r, r);
+    const double t = table[ki & 15];
+    const double res = fma(t, em1, t);
+    const int hi = __double2hiint(res) + (((ki >> 4) + 1000) << 20);
+    return __hiloint2double(hi, __double2loint(res)) * 0x1p-1000;
+}
+
 __device__ __noinline__ double log_slow(double x) { return log(x); }
 
 __device__ __forceinline__ double log_core(double x, const double *__restrict__ table) {
-    const int hi = __double2hiint(x);
-    if (hi < 0x00100000 || hi >= 0x7ff00000) return log_slow(x);   // denormal, 0, < 0, inf, nan
+    int hi = __double2hiint(x);
+    double bias = 0.0;
+    if (hi < 0x00100000) {   // denormal (or 0 / negative, which go to the library)
+        if (!(x > 0.0)) return log_slow(x);
+        x *= 0x1p64;
+        bias = -64.0;
+        hi = __double2hiint(x);
+    } else if (hi >= 0x7ff00000) {
+        return log_slow(x);   // inf, nan
+    }
     const int j = (hi >> 14) & 63;
-    const double e = static_cast<double>((hi >> 20) - 1023);
+    const double e = static_cast<double>((hi >> 20) - 1023) + bias;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
     const double r = fma(m, table[j], -1.0);
     double q = fma(r, c_math.l7, c_math.l6);
@@ -164,6 +194,18 @@ __device__ __forceinline__ double poisson_exponent(double c1, double lg1, double
     const double x = __dsub_rn(__dsub_rn(__dmul_rn(c1, logc2), lg1), c2);
     return x < c_math.log_floor ? c_math.log_floor : x;
 }
+// sum += max(x, L) - L for x = c1*log(c2) - lgamma(c1+1) - c2 and L = log 1e-10, given
+// m1 = -(lgamma(c1+1) + L): one FMA, one add, and the clamp as a test of the sign bit
+// (x < L  <=>  x - L < 0), which keeps it off the FP64 pipe.  The FMA differs from the
+// reference's rounding of x by an ulp of x (~4e-15), far inside the 1e-9 bar.
+__device__ __forceinline__ void add_poisson_excess(double &sum, double c1, double m1, double c2,
+                                                   double logc2) {
+    const double d = fma(c1, logc2, m1) - c2;
+    // sign-bit test + predicated add (the compiler would otherwise add and select twice)
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\t@p add.f64 %0, %0, %2;\n\t}"
+        : "+d"(sum) : "r"(__double2hiint(d)), "d"(d));
+}
+
 __device__ __forceinline__ double poisson_term(double c1, double lg1, double c2, double logc2,
                                                const double *__restrict__ table) {
     return exp_core(poisson_exponent(c1, lg1, c2, logc2), table);
@@ -178,37 +220,106 @@ __device__ __forceinline__ double comp_prob_fast(double d2, const double *__rest
     const double dx = __dsub_rn(d, c_gauss.mu_inter);
     const double ai = -d2 * c_math.inv_two_var_intra;
     const double ae = -(dx * dx) * c_math.inv_two_var_inter;
+    if (!(ae >= -700.0) || !(ai <= 0.0)) return comp_prob_dev(d);   // d > 1.3 or NaN
     // exp() underflows to exactly 0 below -745.14: prob_comp is then 0 / (0 + ge) = 0
-    if (ai < -746.0 && ae >= -700.0) return 0.0;
-    if (ai < -700.0 || ae < -700.0 || !(ai <= 0.0)) return comp_prob_dev(d);
-    const double gi = exp_core(ai, table) * c_math.inv_denom_intra;
+    if (ai < -745.2) return 0.0;
     const double ge = exp_core(ae, table) * c_math.inv_denom_inter;
+    double gi;
+    if (ai >= -700.0) gi = exp_core(ai, table) * c_math.inv_denom_intra;
+    else gi = __ddiv_rn(exp_gradual(ai, table), c_gauss.denom_intra);   // the reference's two roundings
     return __ddiv_rn(gi, gi + ge);
 }
-
 
 __device__ __noinline__ double exp_slow(double x) { return exp(x); }
 
 // log(prob_comp), or NaN when prob_comp is exactly 0 (an underflowed intra Gaussian,
 // d >~ 0.21).  Fast path: log gi is its exponent minus log(sd sqrt(2 pi)), so one table log of
 // gi + ge replaces the division and the log of the quotient.
+// log(prob_comp), or NaN when prob_comp is exactly 0 (an underflowed intra Gaussian,
+// d >~ 0.21).  Fast path: log gi is its exponent minus log(sd sqrt(2 pi)), so one table log of
+// gi + ge replaces the division and the log of the quotient.
 __device__ __forceinline__ double log_comp_prob(double d2, const double *__restrict__ etab,
                                                 const double *__restrict__ ltab,
                                                 bool *domain_error) {
+    const double kNone = __longlong_as_double(0x7ff8000000000000LL);
     const double d = sqrt(d2);
     const double dx = __dsub_rn(d, c_gauss.mu_inter);
     const double ai = -d2 * c_math.inv_two_var_intra;
     const double ae = -(dx * dx) * c_math.inv_two_var_inter;
-    if (ai < -746.0 && ae >= -700.0) return __longlong_as_double(0x7ff8000000000000LL);
-    if (ai < -700.0 || ae < -700.0 || !(ai <= 0.0)) {
+    if (!(ae >= -700.0) || !(ai <= 0.0)) {   // d > 1.3 or NaN: the reference's own sequence
         const double pc = comp_prob_dev(d);
         if (pc != pc) *domain_error = true;
-        if (!(pc > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+        if (!(pc > 0.0)) return kNone;
         return log_core(pc, ltab);
     }
-    const double gi = exp_core(ai, etab) * c_math.inv_denom_intra;
+    if (ai < -745.2) return kNone;           // exp() underflows to exactly 0
     const double ge = exp_core(ae, etab) * c_math.inv_denom_inter;
-    return (ai + c_math.log_inv_denom_intra) - log_core(gi + ge, ltab);
+    if (ai >= -700.0) {
+        const double gi = exp_core(ai, etab) * c_math.inv_denom_intra;
+        return (ai + c_math.log_inv_denom_intra) - log_core(gi + ge, ltab);
+    }
+    // the intra Gaussian is (nearly) denormal: keep the reference's roundings
+    const double gi = __ddiv_rn(exp_gradual(ai, etab), c_gauss.denom_intra);
+    const double pc = __ddiv_rn(gi, gi + ge);
+    if (!(pc > 0.0)) return kNone;
+    return log_core(pc, ltab);
+}
+
+// log of a normal positive double (no range checks).
+__device__ __forceinline__ double log_normal(double x, const double *__restrict__ table) {
+    const int hi = __double2hiint(x);
+    const int j = (hi >> 14) & 63;
+    const double e = static_cast<double>((hi >> 20) - 1023);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double r = fma(m, table[j], -1.0);
+    double q = fma(r, c_math.l7, c_math.l6);
+    q = fma(q, r, c_math.l5);
+    q = fma(q, r, c_math.l4);
+    q = fma(q, r, c_math.l3);
+    q = fma(q, r, -0.5);
+    const double l1p = fma(q, r * r, r);
+    const double head = fma(e, c_math.ln2_hi, table[64 + j]);
+    return head + fma(e, c_math.ln2_lo, l1p);
+}
+
+// The lanes log_comp_prob_warp cannot take through its straight-line path: an intra
+// Gaussian that underflows to 0 (NaN marker), is (nearly) denormal, or d > 1.3 / NaN.
+__device__ __noinline__ double log_comp_prob_special(double d, double ai, double ae,
+                                                      const double *etab, const double *ltab,
+                                                      int32_t *status) {
+    const double kNone = __longlong_as_double(0x7ff8000000000000LL);
+    if (!(ae >= -700.0) || !(ai <= 0.0)) {   // the reference's own sequence
+        const double pc = comp_prob_dev(d);
+        if (pc != pc) atomicOr(status, 1);
+        return (pc > 0.0) ? log_core(pc, ltab) : kNone;
+    }
+    if (ai < -745.2) return kNone;           // exp() underflows to exactly 0
+    const double ge = exp_core(ae, etab) * c_math.inv_denom_inter;
+    const double gi = __ddiv_rn(exp_gradual(ai, etab), c_gauss.denom_intra);
+    const double pc = __ddiv_rn(gi, gi + ge);
+    return (pc > 0.0) ? log_core(pc, ltab) : kNone;
+}
+
+// log(prob_comp) for a whole warp.  prob_comp = gi / (gi + ge) = 1 / (1 + rho) with
+// rho = (sd_i / sd_e) exp(ae - ai), so log prob_comp = -log(1 + rho): one table exp and one
+// table log.  ae - ai >= -1.96 (its minimum, at d = 0), so rho >= 0.021 and 1 + rho loses
+// nothing; the fast path covers ai, ae >= -700 (rho <= 1e303).  The few lanes outside that range
+// -- an intra Gaussian that is denormal or exactly 0, d > 1.3, NaN -- are fixed up under one
+// warp-level branch with the reference's own operation sequence.  NaN = prob_comp is 0.
+__device__ __forceinline__ double log_comp_prob_warp(double d2, const double *__restrict__ etab,
+                                                     const double *__restrict__ ltab,
+                                                     int32_t *status) {
+    const double d = sqrt(d2);
+    const double dx = d - c_gauss.mu_inter;
+    const double ai = -d2 * c_math.inv_two_var_intra;
+    const double ae = -(dx * dx) * c_math.inv_two_var_inter;
+    const bool special = !(ai >= -700.0) || !(ae >= -700.0) || !(ai <= 0.0);
+    const double rho = exp_core(special ? 0.0 : ae - ai, etab) * c_math.sd_ratio;
+    double out = -log_normal(1.0 + rho, ltab);
+    if (__any_sync(0xffffffffu, special)) {
+        if (special) out = log_comp_prob_special(d, ai, ae, etab, ltab, status);
+    }
+    return out;
 }
 
 // ---- coverage terms --------------------------------------------------------------------
@@ -353,7 +464,7 @@ __device__ __forceinline__ void tile_rows(long long *rows, double *norms, const 
     const int tid = threadIdx.x;
     if (tid < kTile) {
         long long row = -1;
-        if (r0 + tid < s.n) row = s.index ? s.index[r0 + tid] : (r0 + tid);
+        if (r0 + tid < s.n) row = s.index ? s.index[s.first + r0 + tid] : (s.first + r0 + tid);
         rows[tid] = row;
         norms[tid] = (want_norm && row >= 0) ? s.norm[row] : 0.0;
     }
@@ -630,14 +741,294 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
     }
 }
 
+// ---- rule C at scale: distance GEMM + probability kernel ---------------------------------------
+// For the big rule-C batches (every long contig against every bin centroid, S <= 30) the work
+// is split in two kernels with different shapes:
+//   dist2_kernel  the d^2 matrix by the DMMA path of pair_kernel (same staging, same fragment
+//                 layout), written to a scratch matrix in HBM (8 bytes per pair, read back once);
+//   prob_kernel   one warp = one contig against 32 bins per pass.  The contig's coverage terms
+//                 are warp-uniform (broadcast reads), the bins' terms sit in shared memory for
+//                 the whole kernel, there is no barrier after the prologue and the kernel needs
+//                 <= 64 registers, so 32 warps per SM hide the FP64 latencies that the
+//                 two-CTA fused kernel exposes.
+// The arithmetic per pair is the same as pair_kernel<RULE_C, LOGSUM>.
+template <int DUMMY>
+__global__ void __launch_bounds__(kPairThreads, 2)
+dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc) {
+    extern __shared__ __align__(16) double sm[];
+    double *stage = sm;                                   // [2 stages][A, B][64][pitch]
+    double *NA = stage + 4 * kChunkDoubles;
+    double *NB = NA + kTile;                              // [2][64]
+    long long *rowA = reinterpret_cast<long long *>(NB + 2 * kTile);
+    long long *rowB = rowA + kTile;                       // [2][64]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = warp >> 1, wc = warp & 1;
+    const int row0 = 16 * wr + g;
+    const int col0 = 32 * wc + 2 * t;
+    const long long a0 = static_cast<long long>(blockIdx.x) * kTile;
+    const long long n_btiles = (B.n + kTile - 1) / kTile;
+    constexpr int kChunks = (MCG_NPROF + kKC - 1) / kKC;
+
+    tile_rows(rowA, NA, A, a0, true);
+    long long bt = blockIdx.y;
+    if (bt < n_btiles) tile_rows(rowB, NB, B, bt * kTile, true);
+    __syncthreads();
+    if (bt < n_btiles) {
+        stage_prof_chunk(stage, A.prof, rowA, 0, kKC);
+        stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB, 0, kKC);
+    }
+    cp_async_commit();
+
+    for (int it = 0; bt < n_btiles; bt += gridDim.y, ++it) {
+        const int cur = it & 1;
+        const long long b0 = bt * kTile;
+        const long long *rows_b = rowB + cur * kTile;
+        const double *norm_b = NB + cur * kTile;
+        const long long bt_next = bt + gridDim.y;
+        const long long left = B.n - b0 - 32 * wc;
+        const int njv = left <= 0 ? 0 : (left >= 32 ? 4 : static_cast<int>((left + 7) >> 3));
+        if (bt_next < n_btiles) tile_rows(rowB + (cur ^ 1) * kTile, NB + (cur ^ 1) * kTile, B,
+                                          bt_next * kTile, true);
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+            if (c + 1 < kChunks) {
+                double *nxt = stage + ((c + 1) & 1) * 2 * kChunkDoubles;
+                const int kc = (c + 1 == kChunks - 1) ? MCG_NPROF - (kChunks - 1) * kKC : kKC;
+                stage_prof_chunk(nxt, A.prof, rowA, (c + 1) * kKC, kc);
+                stage_prof_chunk(nxt + kChunkDoubles, B.prof, rows_b, (c + 1) * kKC, kc);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const double *Ak = stage + (c & 1) * 2 * kChunkDoubles + row0 * kPitch + t;
+            const double *Bk = stage + (c & 1) * 2 * kChunkDoubles + kChunkDoubles +
+                               (32 * wc + g) * kPitch + t;
+            const int ksteps = (c == kChunks - 1) ? (MCG_NPROF - (kChunks - 1) * kKC) / 4 : kKC / 4;
+            if (njv > 0) {
+#pragma unroll 2
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const double a_lo = Ak[4 * ks];
+                    const double a_hi = Ak[8 * kPitch + 4 * ks];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < njv) {
+                            const double b = Bk[8 * j * kPitch + 4 * ks];
+                            dmma(acc[0][j][0], acc[0][j][1], a_lo, b);
+                            dmma(acc[1][j][0], acc[1][j][1], a_hi, b);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (bt_next < n_btiles) {
+            stage_prof_chunk(stage, A.prof, rowA, 0, kKC);
+            stage_prof_chunk(stage + kChunkDoubles, B.prof, rowB + (cur ^ 1) * kTile, 0, kKC);
+        }
+        cp_async_commit();
+        // d^2 = |u|^2 + |v|^2 - 2 u.v, clamped at 0; the scratch matrix is padded to whole tiles
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < njv) {
+                    double2 v;
+                    const double n_a = NA[row0 + 8 * i];
+                    v.x = fma(-2.0, acc[i][j][0], n_a + norm_b[col0 + 8 * j]);
+                    v.y = fma(-2.0, acc[i][j][1], n_a + norm_b[col0 + 8 * j + 1]);
+                    v.x = v.x > 0.0 ? v.x : 0.0;
+                    v.y = v.y > 0.0 ? v.y : 0.0;
+                    *reinterpret_cast<double2 *>(d2out + (a0 + row0 + 8 * i) * ldc + b0 + col0 +
+                                                 8 * j) = v;
+                }
+            }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+constexpr size_t kDistSmem = sizeof(double) * (4 * kChunkDoubles + 3 * kTile) +
+                             sizeof(long long) * 3 * kTile;
+
+constexpr int kProbThreads = 256;
+// prob_kernel keeps one row of 3 S doubles per bin, padded to an odd pitch so that the 32 lanes
+// of a warp (32 different bins, same sample) hit 16 distinct bank pairs twice
+static inline int bin_pitch(int S) { return (3 * S) | 1; }
+constexpr int kProbWarps = kProbThreads / 32;
+
+constexpr int kProbRows = 2;   // contigs per warp iteration: the bins' terms are loaded once for both
+
+// bins [g0, g0 + ncols) of the B side: BT[col][pitch] = (c, log c, m) x S; warp buffers AT.
+__global__ void __launch_bounds__(kProbThreads, 3)
+prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
+            long long g0, int ncols, int ncols_pad, int pitch, ScoreOut out,
+            int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) double sm[];
+    double *ET = sm;                                  // 16
+    double *LT = ET + 16;                             // 128
+    double *AT = LT + 128;                            // [8 warps][2 rows][S][4]
+    double *BT = AT + kProbWarps * kProbRows * 4 * 32;   // [ncols_pad][pitch]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 16) ET[tid] = g_exp_table[tid];
+    if (tid < 128) LT[tid] = g_log_table[tid];
+    for (int idx = tid; idx < ncols_pad * S; idx += kProbThreads) {
+        const int c = idx / S, q = idx - c * S;
+        double bc = 1.0, bl = 0.0, bm = -c_math.log_floor;
+        if (c < ncols) {
+            const long long row = B.index ? B.index[B.first + g0 + c] : (B.first + g0 + c);
+            const long long off = row * S + q;
+            bc = B.cov[off]; bl = B.logc[off]; bm = -(B.lgam[off] + c_math.log_floor);
+        }
+        BT[c * pitch + 3 * q + 0] = bc;
+        BT[c * pitch + 3 * q + 1] = bl;
+        BT[c * pitch + 3 * q + 2] = bm;
+    }
+    __syncthreads();
+
+    double *at = AT + warp * kProbRows * 4 * 32;
+    const long long n_warps = static_cast<long long>(gridDim.x) * kProbWarps;
+    const long long n_iter = (A.n + kProbRows - 1) / kProbRows;
+    const bool last_group = g0 + ncols >= B.n;
+    for (long long it = static_cast<long long>(blockIdx.x) * kProbWarps + warp; it < n_iter;
+         it += n_warps) {
+        const long long r0 = it * kProbRows;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kProbRows; ++k) {
+            // a missing second row repeats the first one; its results are not stored
+            const long long r = r0 + k < A.n ? r0 + k : r0;
+            const long long row = A.index ? A.index[A.first + r] : (A.first + r);
+            if (lane < S) {
+                const long long off = row * S + lane;
+                at[k * 128 + 4 * lane + 0] = A.cov[off];
+                at[k * 128 + 4 * lane + 1] = A.logc[off];
+                at[k * 128 + 4 * lane + 2] = -(A.lgam[off] + c_math.log_floor);
+            }
+        }
+        __syncwarp();
+        double best_w[kProbRows];
+        int best_i[kProbRows];
+        const double *d2row[kProbRows];
+        double dd_next[kProbRows];
+#pragma unroll
+        for (int k = 0; k < kProbRows; ++k) {
+            const long long r = r0 + k < A.n ? r0 + k : r0;
+            best_w[k] = 0.0;
+            best_i[k] = -1;
+            if (g0 > 0) {   // continue from the previous bin group
+                best_w[k] = out.wmin[A.first + r];
+                best_i[k] = out.argmin[A.first + r];
+            }
+            d2row[k] = d2 + r * ldc + g0;
+            dd_next[k] = d2row[k][lane < ncols ? lane : 0];
+        }
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            const int col = c0 + lane;
+            const bool live = col < ncols;
+            const int nxt = col + 32 < ncols ? col + 32 : 0;
+            double log_pc[kProbRows];
+            bool any_pc = false;
+#pragma unroll
+            for (int k = 0; k < kProbRows; ++k) {
+                const double dd = dd_next[k];
+                dd_next[k] = d2row[k][nxt];   // the next pass's distance
+                log_pc[k] = log_comp_prob_warp(dd, ET, LT, status);
+                any_pc = any_pc || (log_pc[k] == log_pc[k]);   // NaN: prob_comp is exactly 0
+            }
+            double tsum[kProbRows];
+#pragma unroll
+            for (int k = 0; k < kProbRows; ++k) tsum[k] = log_pc[k];
+            // when prob_comp is 0 for every pair of the pass the coverage terms are not needed
+            if (__any_sync(0xffffffffu, any_pc)) {
+                double s1[kProbRows], s2[kProbRows];
+#pragma unroll
+                for (int k = 0; k < kProbRows; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
+                const double *bt = BT + (live ? col : 0) * pitch;
+                const double *ap = at;
+#pragma unroll 5
+                for (int q = 0; q < S; ++q) {
+                    const double bc = bt[0], bl = bt[1], bm = bt[2];
+#pragma unroll
+                    for (int k = 0; k < kProbRows; ++k) {
+                        const double ac = ap[k * 128], al = ap[k * 128 + 1], am = ap[k * 128 + 2];
+                        add_poisson_excess(s1[k], ac, am, bc, bl);
+                        add_poisson_excess(s2[k], bc, bm, ac, al);
+                    }
+                    ap += 4;
+                    bt += 3;
+                }
+#pragma unroll
+                for (int k = 0; k < kProbRows; ++k) {
+                    // log prob_cov = min over the two directions of sum_s max(x_s, L)
+                    const double pmin = fma(static_cast<double>(S), c_math.log_floor,
+                                            s1[k] < s2[k] ? s1[k] : s2[k]);
+                    tsum[k] = log_pc[k] + pmin;   // stays NaN when prob_comp is 0
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kProbRows; ++k) {
+                // prob_comp * prob_cov > 0.0 in double arithmetic: certain above e^-744,
+                // impossible below e^-746 (2^-1075 = e^-745.13); in between, multiply
+                bool valid = tsum[k] > -744.0;
+                const bool edge = !valid && tsum[k] >= -746.0;
+                if (__any_sync(0xffffffffu, edge)) {
+                    if (edge) valid = __dmul_rn(exp_slow(log_pc[k]),
+                                                exp_slow(tsum[k] - log_pc[k])) > 0.0;
+                }
+                const double lp = -tsum[k] * c_math.inv_ln10;
+                const double w = (valid && lp != 0.0) ? lp : MCG_MAX_WEIGHT;
+                if (live) {
+                    const int bi = static_cast<int>(g0) + col;
+                    if (out.weights && r0 + k < A.n)
+                        out.weights[(A.first + r0 + k) * B.n + bi] = w;
+                    if (best_i[k] < 0 || w < best_w[k]) { best_w[k] = w; best_i[k] = bi; }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kProbRows; ++k) {
+            // first index of the minimum over the 32 lanes
+            double bw = best_w[k];
+            int bi = best_i[k];
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, bw, m);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+                if (oi >= 0 && (bi < 0 || ow < bw || (ow == bw && oi < bi))) { bw = ow; bi = oi; }
+            }
+            if (lane == 0 && r0 + k < A.n) {
+                // label_prop_utils.py:342-345: None when the minimum is MAX_WEIGHT
+                const bool none = (bi < 0) || (bw == MCG_MAX_WEIGHT);
+                if (last_group) {
+                    if (out.argmin) out.argmin[A.first + r0 + k] = none ? -1 : bi;
+                    if (out.wmin) out.wmin[A.first + r0 + k] = none ? MCG_MAX_WEIGHT : bw;
+                } else {   // carry the running minimum to the next bin group
+                    out.argmin[A.first + r0 + k] = bi;
+                    out.wmin[A.first + r0 + k] = bw;
+                }
+            }
+        }
+    }
+}
+
 // get_tetramer_distance for all pairs in the reference's difference form (diagnostic output of
 // mcg_pair_scores; the scorer itself uses the norm / dot-product form).
 __global__ void pair_distance_kernel(ScoreSide A, ScoreSide B, double *__restrict__ dist) {
     const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i >= A.n * B.n) return;
     const long long qa = i / B.n, qb = i - qa * B.n;
-    const double *u = A.prof + (A.index ? A.index[qa] : qa) * MCG_NPROF;
-    const double *v = B.prof + (B.index ? B.index[qb] : qb) * MCG_NPROF;
+    const double *u = A.prof + (A.index ? A.index[A.first + qa] : A.first + qa) * MCG_NPROF;
+    const double *v = B.prof + (B.index ? B.index[B.first + qb] : B.first + qb) * MCG_NPROF;
     double acc = 0.0;
     for (int k = 0; k < MCG_NPROF; ++k) {
         const double d = u[k] - v[k];
@@ -803,6 +1194,7 @@ static int ensure_gauss(mcg_ctx *ctx) {
     m.inv_denom_inter = 1.0 / g.denom_inter;
     m.inv_ln10 = 1.0 / g.ln10;
     m.log_inv_denom_intra = -log(g.denom_intra);
+    m.sd_ratio = sd_i / sd_e;
     MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_math, &m, sizeof m, 0, cudaMemcpyHostToDevice,
                                           ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -825,6 +1217,66 @@ int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam,
     return MCG_OK;
 }
 
+// The two-kernel rule-C path over row chunks of the A side (the d^2 scratch is bounded).
+static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int S,
+                        const ScoreOut &out, int32_t *d_status) {
+    static bool attr[64] = {};
+    const long long b_tiles = (b.n + kTile - 1) / kTile;
+    const long long ldc = b_tiles * kTile;
+    // bins per shared-memory group of prob_kernel (<= 44 KB of terms), whole warps of columns
+    const int pitch = bin_pitch(S);
+    long long group = (56 * 1024) / (sizeof(double) * pitch);
+    group = (group / 32) * 32;
+    if (group < 32) group = 32;
+    const long long n_groups = (b.n + group - 1) / group;
+    group = ((b.n + n_groups - 1) / n_groups + 31) / 32 * 32;
+    const size_t prob_smem = sizeof(double) * (16 + 128 + kProbWarps * kProbRows * 4 * 32 + pitch * group);
+    if (!(ctx->device < 64 && attr[ctx->device])) {
+        MCG_CUDA(ctx, cudaFuncSetAttribute(dist2_kernel<0>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kDistSmem)));
+        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           96 * 1024));
+        if (ctx->device < 64) attr[ctx->device] = true;
+    }
+    // rows per chunk: <= 512 MiB of scratch, whole tiles
+    long long rows_per_chunk = (512LL << 20) / (sizeof(double) * ldc);
+    rows_per_chunk = (rows_per_chunk / kTile) * kTile;
+    if (rows_per_chunk < kTile) rows_per_chunk = kTile;
+    const long long need_rows = ((a.n < rows_per_chunk ? a.n : rows_per_chunk) + kTile - 1) /
+                                kTile * kTile;
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[5], sizeof(double) * need_rows * ldc));
+    double *d2 = ctx->scratch[5].as<double>();
+    for (long long r0 = 0; r0 < a.n; r0 += rows_per_chunk) {
+        ScoreSide ac = a;
+        ac.first = a.first + r0;
+        ac.n = a.n - r0 < rows_per_chunk ? a.n - r0 : rows_per_chunk;
+        const long long a_tiles = (ac.n + kTile - 1) / kTile;
+        long long gy = (2LL * ctx->sm_count + a_tiles - 1) / a_tiles;
+        if (gy > b_tiles) gy = b_tiles;
+        if (gy < 1) gy = 1;
+        dim3 grid(static_cast<unsigned>(a_tiles), static_cast<unsigned>(gy), 1);
+        dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc);
+        MCG_KERNEL_CHECK(ctx);
+        ScoreOut oc = out;   // outputs are indexed by (first + r): shift them back to the chunk
+        oc.argmin = out.argmin - a.first;
+        oc.wmin = out.wmin - a.first;
+        if (out.weights) oc.weights = out.weights - a.first * b.n;
+        long long blocks = (ac.n + kProbWarps * kProbRows - 1) / (kProbWarps * kProbRows);
+        const long long cap = 3LL * ctx->sm_count * 4;
+        if (blocks > cap) blocks = cap;
+        for (long long g0 = 0; g0 < b.n; g0 += group) {
+            const int ncols = static_cast<int>(b.n - g0 < group ? b.n - g0 : group);
+            const int ncols_pad = (ncols + 31) / 32 * 32;
+            prob_kernel<<<static_cast<unsigned>(blocks), kProbThreads, prob_smem, ctx->stream>>>(
+                ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch, oc, d_status);
+            MCG_KERNEL_CHECK(ctx);
+        }
+    }
+    return MCG_OK;
+}
+
 int mcg_k_row_norms(mcg_ctx *ctx, const double *d_prof, int64_t rows, double *d_norm) {
     if (rows == 0) return MCG_OK;
     row_norms_kernel<<<blocks_for(((rows + 7) / 8) * 32, 256), 256, 0, ctx->stream>>>(d_prof, rows,
@@ -843,6 +1295,10 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
     if (a_tiles > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many query rows");
     dim3 grid(static_cast<unsigned>(a_tiles), 1, 1);
     const bool logsum = n_samples <= 30;
+    // big rule-C batches: distance GEMM + probability kernel (argmin/wmin are needed to
+    // carry the running minimum when the bins do not fit one shared-memory group)
+    if (rule_c && logsum && a.n >= 2048 && out.argmin && out.wmin)
+        return split_rule_c(ctx, a, b, n_samples, out, d_status);
     if (out.dist) {
         pair_distance_kernel<<<blocks_for(a.n * b.n, 128), 128, 0, ctx->stream>>>(a, b, out.dist);
         MCG_KERNEL_CHECK(ctx);

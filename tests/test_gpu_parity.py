@@ -253,7 +253,10 @@ def test_rules_a_b_golden(ctx, score):
 
 
 @pytest.mark.parametrize("S,B,n", [(1, 7, 300), (10, 200, 1000), (30, 40, 300), (31, 40, 300),
-                                   (50, 70, 333), (100, 33, 150)])
+                                   (50, 70, 333), (100, 33, 150),
+                                   # >= 2048 queries take the two-kernel rule-C path; 300 bins
+                                   # need two shared-memory groups there
+                                   (3, 40, 2100), (10, 300, 2500), (30, 70, 2200)])
 def test_rule_c_vs_oracle(ctx, S, B, n):
     """Seeded synthetic contig tables at sizes the oracle finishes in seconds, including
     S > 32 where floor^S underflows and the MAX_WEIGHT / None paths trigger."""
