@@ -31,9 +31,9 @@
 
 namespace {
 
-constexpr int kScanWarps = 8;
+constexpr int kScanWarps = 27;      // 27 x 8 KB tables + alignment slack = 223 KB: one CTA per SM
 constexpr int kScanThreads = kScanWarps * 32;
-constexpr int kScanCtasPerSm = 3;
+constexpr int kScanCtasPerSm = 1;
 constexpr uint32_t kTableBytes = 8192;   // 256 codes x 32 lanes x 1 byte
 
 __device__ uint8_t g_canon_x[256];   // window code x (reversed field order) -> canonical slot
@@ -155,6 +155,11 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
     const uint32_t tab = ((smem_u32(smem_raw) + kTableBytes - 1u) & ~(kTableBytes - 1u)) +
                          warp * kTableBytes;
     const uint32_t lanebase = tab + lane * 4u;
+    {   // the alignment slack assumes the dynamic window starts >= 1 KB into shared memory
+        uint32_t dyn_size;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
+        if (tab + kTableBytes > smem_u32(smem_raw) + dyn_size) __trap();
+    }
 
 #pragma unroll 8
     for (int r = 0; r < 64; ++r) sts_u32(lanebase + r * 128u, 0u);
@@ -457,7 +462,7 @@ int mcg_k_scan(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d_meta,
     MCG_TRY(mcg_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long)));
     MCG_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned long long),
                                   ctx->stream));
-    const size_t smem = kScanWarps * kTableBytes + kTableBytes;   // + alignment slack
+    const size_t smem = kScanWarps * kTableBytes + kTableBytes - 1024;   // + alignment slack
     static bool attr_set[64] = {};
     if (!(ctx->device < 64 && attr_set[ctx->device])) {
         MCG_CUDA(ctx, cudaFuncSetAttribute(scan_kernel,
