@@ -34,8 +34,12 @@ if ROOT not in sys.path:
 N_CONTIGS = int(os.environ.get("MCG_BENCH_CONTIGS", 100000))
 N_SAMPLES = int(os.environ.get("MCG_BENCH_SAMPLES", 10))
 N_BINS = int(os.environ.get("MCG_BENCH_BINS", 200))
-WORKLOAD = "synthetic metaSPAdes-style %dk contigs (1-50 kb), %d samples, %d bins per GPU" % (
-    N_CONTIGS // 1000, N_SAMPLES, N_BINS)
+# length model: "spades" 1-50 kb log-uniform (configs[1], the default), "megahit" lognormal
+# ~3 kb (configs[2]), "flye" 10 kb-5 Mb (configs[3]); the non-default ones are for checks only
+LENGTH_KIND = os.environ.get("MCG_BENCH_KIND", "spades")
+WORKLOAD = "synthetic %s-style %dk contigs, %d samples, %d bins per GPU" % (
+    {"spades": "metaSPAdes (1-50 kb)", "megahit": "MEGAHIT (>= 1 kb, ~3 kb mean)",
+     "flye": "Flye (10 kb-5 Mb)"}[LENGTH_KIND], N_CONTIGS // 1000, N_SAMPLES, N_BINS)
 METRIC = "contigs/sec featurise+score"
 
 
@@ -46,7 +50,7 @@ def workload_tables(seed, n_contigs, n_samples, n_bins):
     dinuc, abundance = synth.genome_tables(rng, n_bins, n_samples)
     trans = dinuc.reshape(n_bins, 4, 4)
     trans = (trans / trans.sum(axis=2, keepdims=True)).astype(np.float32)
-    lengths = synth.sample_lengths(rng, n_contigs, "spades")
+    lengths = synth.sample_lengths(rng, n_contigs, LENGTH_KIND)
     genome_of = rng.integers(0, n_bins, n_contigs).astype(np.int32)
     offsets = np.zeros(n_contigs + 1, dtype=np.int64)
     np.cumsum(lengths, out=offsets[1:])

@@ -814,7 +814,21 @@ dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc
             const double *Bk = stage + (c & 1) * 2 * kChunkDoubles + kChunkDoubles +
                                (32 * wc + g) * kPitch + t;
             const int ksteps = (c == kChunks - 1) ? (MCG_NPROF - (kChunks - 1) * kKC) / 4 : kKC / 4;
-            if (njv > 0) {
+            if (njv == 4 && ksteps == kKC / 4) {
+                // the common case, fully unrolled: all fragment loads of the chunk can be in
+                // flight ahead of the DMMAs
+#pragma unroll
+                for (int ks = 0; ks < kKC / 4; ++ks) {
+                    const double a_lo = Ak[4 * ks];
+                    const double a_hi = Ak[8 * kPitch + 4 * ks];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double b = Bk[8 * j * kPitch + 4 * ks];
+                        dmma(acc[0][j][0], acc[0][j][1], a_lo, b);
+                        dmma(acc[1][j][0], acc[1][j][1], a_hi, b);
+                    }
+                }
+            } else if (njv > 0) {
 #pragma unroll 2
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const double a_lo = Ak[4 * ks];
