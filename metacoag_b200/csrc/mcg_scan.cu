@@ -127,21 +127,20 @@ __device__ __forceinline__ void count_partial(uint32_t lo, uint32_t hi, uint32_t
     }
 }
 
-__device__ __forceinline__ void emit_run(uint32_t *__restrict__ counts, int contig, uint32_t a0,
-                                         uint32_t a1, uint32_t b0, uint32_t b1, uint32_t canA,
-                                         uint32_t canB) {
-    if (contig < 0) return;
-    uint32_t *row = counts + static_cast<int64_t>(contig) * MCG_NPROF;
-    // word byte k holds code 4*row + k; a0 = bytes 0|2, a1 = bytes 1|3 (16-bit fields)
-    uint32_t v;
-    v = a0 & 0xFFFFu; if (v) atomicAdd(row + (canA & 0xFFu), v);
-    v = a1 & 0xFFFFu; if (v) atomicAdd(row + ((canA >> 8) & 0xFFu), v);
-    v = a0 >> 16;     if (v) atomicAdd(row + ((canA >> 16) & 0xFFu), v);
-    v = a1 >> 16;     if (v) atomicAdd(row + (canA >> 24), v);
-    v = b0 & 0xFFFFu; if (v) atomicAdd(row + (canB & 0xFFu), v);
-    v = b1 & 0xFFFFu; if (v) atomicAdd(row + ((canB >> 8) & 0xFFu), v);
-    v = b0 >> 16;     if (v) atomicAdd(row + ((canB >> 16) & 0xFFu), v);
-    v = b1 >> 16;     if (v) atomicAdd(row + (canB >> 24), v);
+// The lane's eight code totals (table rows lane and lane + 32, bytes 0..3) of one contig go to
+// the contig's row of `counts`, folded onto the canonical slots.
+__device__ __forceinline__ void emit_held(uint32_t *__restrict__ counts, int contig,
+                                          uint32_t (&acc)[8], uint32_t canA, uint32_t canB) {
+    if (contig >= 0) {
+        uint32_t *row = counts + static_cast<int64_t>(contig) * MCG_NPROF;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (acc[b]) atomicAdd(row + ((canA >> (8 * b)) & 0xFFu), acc[b]);
+            if (acc[4 + b]) atomicAdd(row + ((canB >> (8 * b)) & 0xFFu), acc[4 + b]);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b] = 0;
 }
 
 __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
@@ -173,11 +172,29 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
         canB |= static_cast<uint32_t>(g_canon_x[128 + 4 * lane + b]) << (8 * b);
     }
 
+    // A warp takes strips of kStrip consecutive tiles and keeps the totals of the contig it is
+    // in (`held`) in registers across tiles: a long contig costs one set of global reductions
+    // per strip instead of one per tile, which otherwise serialise on its 136 addresses.
+    constexpr int kStrip = 4;
+    uint32_t acc[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b] = 0;
+    int held = -1;
     const long long n_tiles = (n_seg + 31) >> 5;
+    unsigned long long tile = 0;
+    int in_strip = kStrip;
     for (;;) {
-        unsigned long long tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1ULL);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (in_strip == kStrip) {
+            // the totals do not travel between strips: the next strip is somewhere else
+            emit_held(counts, held, acc, canA, canB);
+            held = -1;
+            if (lane == 0) tile = atomicAdd(tile_counter, 1ULL) * kStrip;
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            in_strip = 0;
+        } else {
+            ++tile;
+        }
+        ++in_strip;
         if (static_cast<long long>(tile) >= n_tiles) break;
 
         const long long g = static_cast<long long>(tile) * 32 + lane;
@@ -260,10 +277,17 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
                 b1 += (wB >> 8) & 0x00FF00FFu;
                 if (++col == c1) col = c0;
             }
-            emit_run(counts, run_contig, a0, a1, b0, b1, canA, canB);
+            if (run_contig != held) {
+                emit_held(counts, held, acc, canA, canB);
+                held = run_contig;
+            }
+            // word byte k holds code 4*row + k; a0 = bytes 0|2, a1 = bytes 1|3 (16-bit fields)
+            acc[0] += a0 & 0xFFFFu; acc[1] += a1 & 0xFFFFu; acc[2] += a0 >> 16; acc[3] += a1 >> 16;
+            acc[4] += b0 & 0xFFFFu; acc[5] += b1 & 0xFFFFu; acc[6] += b0 >> 16; acc[7] += b1 >> 16;
         }
         __syncwarp();
     }
+    emit_held(counts, held, acc, canA, canB);
 }
 
 // freqs = counts / max(1, sum(counts)) with sum(counts) = windows  (feature_utils.py:70)
