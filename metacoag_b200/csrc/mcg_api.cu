@@ -145,6 +145,9 @@ extern "C" mcg_ctx *mcg_create(int device) {
         return nullptr;
     }
     ctx->stream = ctx->own_stream;
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->copy_start, cudaEventDisableTiming);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i) cudaEventCreate(&ctx->ev[i]);
     if (mcg_reserve(ctx, ctx->status, 4 * sizeof(int32_t)) != MCG_OK) {
         delete ctx;
@@ -170,6 +173,10 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+    if (ctx->copy_start) cudaEventDestroy(ctx->copy_start);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -273,8 +280,32 @@ static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t
         if (encoding == MCG_ENC_ASCII) {
             MCG_TRY(mcg_reserve(ctx, ctx->ascii, static_cast<size_t>(n_bases) + 256));
             MCG_TRY(mcg_reserve(ctx, ctx->offsets, sizeof(int64_t) * (n + 1)));
-            MCG_TRY(h2d(ctx, ctx->ascii.p, bases + offsets[0], static_cast<size_t>(n_bases)));
             MCG_TRY(h2d(ctx, ctx->offsets.p, offsets, sizeof(int64_t) * (n + 1)));
+            // The bases go up in chunks of whole contigs (~32 MB) on a second stream; the
+            // pack kernel of chunk i runs while chunk i+1 is still on the wire.
+            MCG_CUDA(ctx, cudaEventRecord(ctx->copy_start, ctx->stream));
+            MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_start, 0));
+            const int64_t chunk_bytes = 32 << 20;
+            int64_t c0 = 0;
+            int slot = 0;
+            while (c0 < n) {
+                int64_t c1 = c0;
+                while (c1 < n && offsets[c1] - offsets[c0] < chunk_bytes) ++c1;
+                const size_t bytes = static_cast<size_t>(offsets[c1] - offsets[c0]);
+                if (bytes)
+                    MCG_CUDA(ctx, cudaMemcpyAsync(ctx->ascii.as<uint8_t>() + offsets[c0],
+                                                  bases + offsets[c0], bytes,
+                                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+                MCG_CUDA(ctx, cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream));
+                MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0));
+                const int64_t w0 = meta[c0].pk_word;
+                const int64_t w1 = c1 < n ? meta[c1].pk_word : n_words;
+                MCG_TRY(mcg_k_pack_ascii(ctx, ctx->ascii.as<uint8_t>(), ctx->offsets.as<int64_t>(),
+                                         ctx->meta.as<ContigMeta>(), n, w0, w1 - w0,
+                                         ctx->packed.as<uint32_t>()));
+                slot = (slot + 1) & 3;
+                c0 = c1;
+            }
         } else {
             MCG_TRY(h2d(ctx, ctx->packed.p, bases, sizeof(uint32_t) * n_words));
         }
@@ -282,12 +313,6 @@ static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t
     // the words after the last contig are read as halo / by idle lanes
     MCG_CUDA(ctx, cudaMemsetAsync(ctx->packed.as<uint32_t>() + n_words, 0, sizeof(uint32_t) * 32,
                                   ctx->stream));
-    if (encoding == MCG_ENC_ASCII) {
-        TimerScope t(ctx, T_PACK);
-        MCG_TRY(mcg_k_pack_ascii(ctx, ctx->ascii.as<uint8_t>(), ctx->offsets.as<int64_t>(),
-                                 ctx->meta.as<ContigMeta>(), n, n_words,
-                                 ctx->packed.as<uint32_t>()));
-    }
     {
         TimerScope t(ctx, T_OTHER);
         MCG_TRY(mcg_k_fill_seg_contig(ctx, ctx->meta.as<ContigMeta>(), n, n_seg,

@@ -37,6 +37,9 @@ struct mcg_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of contig chunks, overlapped with packing
+    cudaEvent_t copy_ev[4] = {};
+    cudaEvent_t copy_start = nullptr;
     std::mutex mu;
     std::string err;
 
@@ -127,7 +130,7 @@ struct TimerScope {
 
 // mcg_scan.cu
 int mcg_k_pack_ascii(mcg_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_offsets,
-                     const ContigMeta *d_meta, int64_t n_contigs, int64_t n_words,
+                     const ContigMeta *d_meta, int64_t n_contigs, int64_t word0, int64_t n_words,
                      uint32_t *d_packed);
 int mcg_k_fill_seg_contig(mcg_ctx *ctx, const ContigMeta *d_meta, int64_t n_contigs,
                           int64_t n_seg, int32_t *d_seg_contig);

@@ -334,9 +334,10 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w) {
 __global__ void pack_ascii_kernel(const uint8_t *__restrict__ ascii,
                                   const int64_t *__restrict__ offsets,
                                   const ContigMeta *__restrict__ meta, long long n_contigs,
-                                  long long n_units, uint32_t *__restrict__ packed) {
-    const long long u = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (u >= n_units) return;
+                                  long long unit0, long long n_units,
+                                  uint32_t *__restrict__ packed) {
+    const long long u = unit0 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (u >= unit0 + n_units) return;
     const long long word = 4 * u;
     long long lo = 0, hi = n_contigs;   // largest c with pk_word[c] <= word
     while (hi - lo > 1) {
@@ -453,14 +454,14 @@ static int ensure_canon_table(mcg_ctx *ctx) {
 }
 
 int mcg_k_pack_ascii(mcg_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_offsets,
-                     const ContigMeta *d_meta, int64_t n_contigs, int64_t n_words,
+                     const ContigMeta *d_meta, int64_t n_contigs, int64_t word0, int64_t n_words,
                      uint32_t *d_packed) {
-    const int64_t n_units = n_words / 4;
+    const int64_t unit0 = word0 / 4, n_units = n_words / 4;
     if (n_units == 0 || n_contigs == 0) return MCG_OK;
     const int threads = 256;
     const int64_t blocks = (n_units + threads - 1) / threads;
     pack_ascii_kernel<<<static_cast<unsigned>(blocks), threads, 0, ctx->stream>>>(
-        d_ascii, d_offsets, d_meta, n_contigs, n_units, d_packed);
+        d_ascii, d_offsets, d_meta, n_contigs, unit0, n_units, d_packed);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }
