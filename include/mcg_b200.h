@@ -174,8 +174,10 @@ int mcg_get_assignments(mcg_ctx *ctx, int32_t *argmin, double *wmin);
 
 /* Per-kernel device times of the last mcg_step_resident / mcg_featurise_score,
  * measured with CUDA events on the launching stream when profiling is on.
- * Slots: 0 pack, 1 scan, 2 normalise, 3 coverage terms, 4 score, 5 h2d, 6 d2h. */
-#define MCG_N_TIMERS 8
+ * Slots: 0 pack, 1 scan, 2 normalise (+ row norms), 3 coverage terms, 4 score (all scoring
+ * kernels), 5 h2d (+ overlapped packing), 6 d2h, 7 other, 8 distance GEMM, 9 probability
+ * kernel (8 and 9 are the two halves of slot 4 on the large rule-C path). */
+#define MCG_N_TIMERS 10
 int mcg_profile(mcg_ctx *ctx, int on);
 int mcg_timings(mcg_ctx *ctx, float *ms /* [MCG_N_TIMERS] */, int64_t *launches);
 

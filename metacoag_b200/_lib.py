@@ -15,8 +15,9 @@ NPROF = 136
 MAX_WEIGHT = sys.float_info.max
 ENC_ASCII, ENC_2BIT = 0, 1
 RULE_A, RULE_B = 0, 1
-N_TIMERS = 8
-TIMER_NAMES = ("pack", "scan", "normalise", "cov_terms", "score", "h2d", "d2h", "other")
+N_TIMERS = 10
+TIMER_NAMES = ("pack", "scan", "normalise", "cov_terms", "score", "h2d", "d2h", "other",
+               "distance", "probability")
 
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_DOMAIN, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 

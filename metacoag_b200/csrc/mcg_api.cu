@@ -337,13 +337,12 @@ static int scan_locked(mcg_ctx *ctx) {
                            ctx->seg_contig.as<int32_t>(), ctx->n_seg, n,
                            ctx->counts.as<uint32_t>()));
     }
+    MCG_TRY(mcg_reserve(ctx, ctx->prof_norm, sizeof(double) * std::max<int64_t>(n, 1)));
     {
         TimerScope t(ctx, T_NORM);
-        MCG_TRY(mcg_k_normalise(ctx, ctx->counts.as<uint32_t>(), ctx->meta.as<ContigMeta>(), n,
-                                ctx->prof.as<double>()));
+        MCG_TRY(mcg_k_normalise_norms(ctx, ctx->counts.as<uint32_t>(), ctx->meta.as<ContigMeta>(),
+                                      n, ctx->prof.as<double>(), ctx->prof_norm.as<double>()));
     }
-    MCG_TRY(mcg_reserve(ctx, ctx->prof_norm, sizeof(double) * std::max<int64_t>(n, 1)));
-    MCG_TRY(mcg_k_row_norms(ctx, ctx->prof.as<double>(), n, ctx->prof_norm.as<double>()));
     ctx->n_prof = n;
     return MCG_OK;
 }

@@ -30,7 +30,7 @@ struct __align__(16) ContigMeta {
     int32_t nwin;       // tetramer windows = max(0, len - 3)
 };
 
-enum { T_PACK = 0, T_SCAN, T_NORM, T_COV, T_SCORE, T_H2D, T_D2H, T_OTHER };
+enum { T_PACK = 0, T_SCAN, T_NORM, T_COV, T_SCORE, T_H2D, T_D2H, T_OTHER, T_DIST, T_PROB };
 
 struct mcg_ctx {
     int device = 0;
@@ -164,6 +164,8 @@ struct ScoreOut {
 };
 int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam, int64_t count);
 int mcg_k_row_norms(mcg_ctx *ctx, const double *d_prof, int64_t rows, double *d_norm);
+int mcg_k_normalise_norms(mcg_ctx *ctx, const uint32_t *d_counts, const ContigMeta *d_meta,
+                          int64_t rows, double *d_prof, double *d_norm);
 int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samples,
                 const ScoreOut &out, int32_t *d_status);
 int mcg_k_aggregate_members(mcg_ctx *ctx, const double *d_lp, int64_t nq, int64_t nm,

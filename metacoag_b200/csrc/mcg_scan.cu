@@ -68,49 +68,48 @@ __device__ __forceinline__ uint4 ldg_u4(const uint32_t *p) {
 }
 
 // One window whose code starts at bit 2*I of the 64-bit value hi:lo.
-//   y: the window shifted so that code bits [2,8) sit at address bits [7,13)
-//   z: the window at bit 0; its low two bits select the byte inside the word
+//   z: the window at bit 0 (one funnel shift); its low two bits select the byte in the word
+//   y = z << 5: code bits [2,8) at address bits [7,13)
+// Every LOP3 / SHF / IADD shares the ALU pipe at one warp instruction per two cycles, which is
+// what bounds this loop; the shift by 5 and the "+ 1" are therefore written as multiply-adds
+// (`one` is a register the compiler cannot fold), which issue to the FMA pipe instead.
 template <int I>
-__device__ __forceinline__ uint32_t window_addr(uint32_t lo, uint32_t hi, uint32_t lanebase) {
-    uint32_t y, z;
-    if constexpr (2 * I >= 5)
-        y = __funnelshift_r(lo, hi, static_cast<uint32_t>(2 * I - 5));
-    else
-        y = lo << static_cast<uint32_t>(5 - 2 * I);
+__device__ __forceinline__ void count_window(uint32_t lo, uint32_t hi, uint32_t lanebase,
+                                             uint32_t one) {
+    uint32_t z;
     if constexpr (I == 0)
         z = lo;
     else
         z = __funnelshift_r(lo, hi, static_cast<uint32_t>(2 * I));
-    return and_or(z, 3u, and_or(y, 0x1F80u, lanebase));
-}
-
-template <int I>
-__device__ __forceinline__ void count_window(uint32_t lo, uint32_t hi, uint32_t lanebase) {
-    const uint32_t addr = window_addr<I>(lo, hi, lanebase);
-    sts_u8(addr, lds_u8(addr) + 1u);
+    uint32_t y;
+    asm("mul.lo.u32 %0, %1, 32;" : "=r"(y) : "r"(z));
+    const uint32_t addr = and_or(z, 3u, and_or(y, 0x1F80u, lanebase));
+    uint32_t v = lds_u8(addr);
+    asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(v) : "r"(one));
+    sts_u8(addr, v);
 }
 
 // 16 windows starting in word `lo` (the last three reach into `hi`).  When `divert` is
 // set the 16th window goes to global memory instead of the byte counter.
 __device__ __forceinline__ void count_word(uint32_t lo, uint32_t hi, uint32_t lanebase,
-                                           bool divert, uint32_t *row) {
-    count_window<0>(lo, hi, lanebase);
-    count_window<1>(lo, hi, lanebase);
-    count_window<2>(lo, hi, lanebase);
-    count_window<3>(lo, hi, lanebase);
-    count_window<4>(lo, hi, lanebase);
-    count_window<5>(lo, hi, lanebase);
-    count_window<6>(lo, hi, lanebase);
-    count_window<7>(lo, hi, lanebase);
-    count_window<8>(lo, hi, lanebase);
-    count_window<9>(lo, hi, lanebase);
-    count_window<10>(lo, hi, lanebase);
-    count_window<11>(lo, hi, lanebase);
-    count_window<12>(lo, hi, lanebase);
-    count_window<13>(lo, hi, lanebase);
-    count_window<14>(lo, hi, lanebase);
+                                           uint32_t one, bool divert, uint32_t *row) {
+    count_window<0>(lo, hi, lanebase, one);
+    count_window<1>(lo, hi, lanebase, one);
+    count_window<2>(lo, hi, lanebase, one);
+    count_window<3>(lo, hi, lanebase, one);
+    count_window<4>(lo, hi, lanebase, one);
+    count_window<5>(lo, hi, lanebase, one);
+    count_window<6>(lo, hi, lanebase, one);
+    count_window<7>(lo, hi, lanebase, one);
+    count_window<8>(lo, hi, lanebase, one);
+    count_window<9>(lo, hi, lanebase, one);
+    count_window<10>(lo, hi, lanebase, one);
+    count_window<11>(lo, hi, lanebase, one);
+    count_window<12>(lo, hi, lanebase, one);
+    count_window<13>(lo, hi, lanebase, one);
+    count_window<14>(lo, hi, lanebase, one);
     if (!divert) {
-        count_window<15>(lo, hi, lanebase);
+        count_window<15>(lo, hi, lanebase, one);
     } else {
         const uint32_t x = __funnelshift_r(lo, hi, 30) & 0xFFu;
         atomicAdd(row + g_canon_x[x], 1u);
@@ -154,6 +153,7 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
     const uint32_t tab = ((smem_u32(smem_raw) + kTableBytes - 1u) & ~(kTableBytes - 1u)) +
                          warp * kTableBytes;
     const uint32_t lanebase = tab + lane * 4u;
+    const uint32_t one = n_seg > 0 ? 1u : 0u;   // a 1 the compiler has to keep in a register
     {   // the alignment slack assumes the dynamic window starts >= 1 KB into shared memory
         uint32_t dyn_size;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
@@ -234,13 +234,13 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
             const uint32_t w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
             const uint32_t w4 = (gi < 3) ? nxt.x : halo;
             const int j = 4 * gi;
-            if (j + 0 < nfull) count_word(w0, w1, lanebase, false, row);
+            if (j + 0 < nfull) count_word(w0, w1, lanebase, one, false, row);
             else if (j + 0 == nfull) count_partial(w0, w1, lanebase, rem);
-            if (j + 1 < nfull) count_word(w1, w2, lanebase, false, row);
+            if (j + 1 < nfull) count_word(w1, w2, lanebase, one, false, row);
             else if (j + 1 == nfull) count_partial(w1, w2, lanebase, rem);
-            if (j + 2 < nfull) count_word(w2, w3, lanebase, false, row);
+            if (j + 2 < nfull) count_word(w2, w3, lanebase, one, false, row);
             else if (j + 2 == nfull) count_partial(w2, w3, lanebase, rem);
-            if (j + 3 < nfull) count_word(w3, w4, lanebase, gi == 3, row);
+            if (j + 3 < nfull) count_word(w3, w4, lanebase, one, gi == 3, row);
             else if (j + 3 == nfull) count_partial(w3, w4, lanebase, rem);
             cur = nxt;
             nxt = nn;

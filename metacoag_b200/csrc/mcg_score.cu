@@ -68,9 +68,12 @@ __device__ double lgamma_cpython(double x) {
             den = __dadd_rn(__dmul_rn(den, x), c_lanczos_den[i]);
         }
     } else {
+        // CPython divides by x at every step; multiplying by 1/x with an FMA differs from
+        // that by a couple of ulp of the sums (checked against math.lgamma at 5e-15)
+        const double rx = __ddiv_rn(1.0, x);
         for (int i = 0; i < 13; ++i) {
-            num = __dadd_rn(__ddiv_rn(num, x), c_lanczos_num[i]);
-            den = __dadd_rn(__ddiv_rn(den, x), c_lanczos_den[i]);
+            num = fma(num, rx, c_lanczos_num[i]);
+            den = fma(den, rx, c_lanczos_den[i]);
         }
     }
     double r = __dsub_rn(log(__ddiv_rn(num, den)), g);
@@ -338,20 +341,35 @@ __global__ void cov_terms_kernel(double *__restrict__ cov, double *__restrict__ 
 }
 
 // ||row||^2 of a [rows,136] table.  It goes through the same DMMA k-step sequence as the u.v of
-// pair_kernel, so that for two bitwise-equal rows |u|^2 + |v|^2 - 2 u.v is exactly 0, as the
-// reference's difference form is: near d = 0 the inter-species Gaussian is linear in d =
-// sqrt(d^2), and a d^2 of 1e-17 instead of 0 would already move prob_comp by 4e-9.
+// pair_kernel / dist2_kernel, so that for two bitwise-equal rows |u|^2 + |v|^2 - 2 u.v is exactly
+// 0, as the reference's difference form is: near d = 0 the inter-species Gaussian is linear in
+// d = sqrt(d^2), and a d^2 of 1e-17 instead of 0 would already move prob_comp by 4e-9.
 // One warp per 8 rows; the diagonal of the 8 x 8 product holds the norms.
-__global__ void row_norms_kernel(const double *__restrict__ prof, long long rows,
-                                 double *__restrict__ norm) {
+// With `counts` given, the rows are first produced from the scan counts
+// (prof = counts / max(1, windows), feature_utils.py:70, IEEE division) and written out.
+__global__ void row_norms_kernel(const double *__restrict__ prof_in,
+                                 const uint32_t *__restrict__ counts,
+                                 const ContigMeta *__restrict__ meta, double *__restrict__ prof_out,
+                                 long long rows, double *__restrict__ norm) {
     const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const long long row = warp * 8 + g;
     if (warp * 8 >= rows) return;
-    const double *p = prof + (row < rows ? row : rows - 1) * MCG_NPROF + t;
+    const long long r = row < rows ? row : rows - 1;
+    double denom = 1.0;
+    if (counts) {
+        const int nwin = meta[r].nwin;
+        denom = static_cast<double>(nwin > 1 ? nwin : 1);
+    }
     double c0 = 0.0, c1 = 0.0;
     for (int k0 = 0; k0 < MCG_NPROF; k0 += 4) {
-        const double a = p[k0];
+        double a;
+        if (counts) {
+            a = __ddiv_rn(static_cast<double>(counts[r * MCG_NPROF + k0 + t]), denom);
+            if (row < rows) prof_out[r * MCG_NPROF + k0 + t] = a;
+        } else {
+            a = prof_in[r * MCG_NPROF + k0 + t];
+        }
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                      : "+d"(c0), "+d"(c1) : "d"(a), "d"(a));
     }
@@ -1271,7 +1289,9 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         if (gy > b_tiles) gy = b_tiles;
         if (gy < 1) gy = 1;
         dim3 grid(static_cast<unsigned>(a_tiles), static_cast<unsigned>(gy), 1);
+        mcg_timer_begin(ctx, T_DIST);
         dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc);
+        mcg_timer_end(ctx, T_DIST);
         MCG_KERNEL_CHECK(ctx);
         ScoreOut oc = out;   // outputs are indexed by (first + r): shift them back to the chunk
         oc.argmin = out.argmin - a.first;
@@ -1280,6 +1300,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         long long blocks = (ac.n + kProbWarps * kProbRows - 1) / (kProbWarps * kProbRows);
         const long long cap = 3LL * ctx->sm_count * 4;
         if (blocks > cap) blocks = cap;
+        mcg_timer_begin(ctx, T_PROB);
         for (long long g0 = 0; g0 < b.n; g0 += group) {
             const int ncols = static_cast<int>(b.n - g0 < group ? b.n - g0 : group);
             const int ncols_pad = (ncols + 31) / 32 * 32;
@@ -1287,14 +1308,25 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
                 ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch, oc, d_status);
             MCG_KERNEL_CHECK(ctx);
         }
+        mcg_timer_end(ctx, T_PROB);
     }
     return MCG_OK;
 }
 
 int mcg_k_row_norms(mcg_ctx *ctx, const double *d_prof, int64_t rows, double *d_norm) {
     if (rows == 0) return MCG_OK;
-    row_norms_kernel<<<blocks_for(((rows + 7) / 8) * 32, 256), 256, 0, ctx->stream>>>(d_prof, rows,
-                                                                                      d_norm);
+    row_norms_kernel<<<blocks_for(((rows + 7) / 8) * 32, 256), 256, 0, ctx->stream>>>(
+        d_prof, nullptr, nullptr, nullptr, rows, d_norm);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+// counts -> normalised profiles and their squared norms in one pass
+int mcg_k_normalise_norms(mcg_ctx *ctx, const uint32_t *d_counts, const ContigMeta *d_meta,
+                          int64_t rows, double *d_prof, double *d_norm) {
+    if (rows == 0) return MCG_OK;
+    row_norms_kernel<<<blocks_for(((rows + 7) / 8) * 32, 256), 256, 0, ctx->stream>>>(
+        nullptr, d_counts, d_meta, d_prof, rows, d_norm);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }
