@@ -771,7 +771,7 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
 //                 two-CTA fused kernel exposes.
 // The arithmetic per pair is the same as pair_kernel<RULE_C, LOGSUM>.
 template <int DUMMY>
-__global__ void __launch_bounds__(kPairThreads, 2)
+__global__ void __launch_bounds__(kPairThreads, 3)
 dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc) {
     extern __shared__ __align__(16) double sm[];
     double *stage = sm;                                   // [2 stages][A, B][64][pitch]
@@ -900,7 +900,7 @@ constexpr int kProbWarps = kProbThreads / 32;
 constexpr int kProbRows = 2;   // contigs per warp iteration: the bins' terms are loaded once for both
 
 // bins [g0, g0 + ncols) of the B side: BT[col][pitch] = (c, log c, m) x S; warp buffers AT.
-__global__ void __launch_bounds__(kProbThreads, 3)
+__global__ void __launch_bounds__(kProbThreads, 4)
 prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
             long long g0, int ncols, int ncols_pad, int pitch, ScoreOut out,
             int32_t *__restrict__ status) {
@@ -908,26 +908,25 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
     double *ET = sm;                                  // 16
     double *LT = ET + 16;                             // 128
     double *AT = LT + 128;                            // [8 warps][2 rows][S][4]
-    double *BT = AT + kProbWarps * kProbRows * 4 * 32;   // [ncols_pad][pitch]
+    const int at_row = 4 * S;
+    double *BT = AT + kProbWarps * kProbRows * at_row;   // [ncols][pitch]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 16) ET[tid] = g_exp_table[tid];
     if (tid < 128) LT[tid] = g_log_table[tid];
-    for (int idx = tid; idx < ncols_pad * S; idx += kProbThreads) {
+    for (int idx = tid; idx < ncols * S; idx += kProbThreads) {
         const int c = idx / S, q = idx - c * S;
-        double bc = 1.0, bl = 0.0, bm = -c_math.log_floor;
-        if (c < ncols) {
-            const long long row = B.index ? B.index[B.first + g0 + c] : (B.first + g0 + c);
-            const long long off = row * S + q;
-            bc = B.cov[off]; bl = B.logc[off]; bm = -(B.lgam[off] + c_math.log_floor);
-        }
+        const long long row = B.index ? B.index[B.first + g0 + c] : (B.first + g0 + c);
+        const long long off = row * S + q;
+        const double bc = B.cov[off], bl = B.logc[off];
+        const double bm = -(B.lgam[off] + c_math.log_floor);
         BT[c * pitch + 3 * q + 0] = bc;
         BT[c * pitch + 3 * q + 1] = bl;
         BT[c * pitch + 3 * q + 2] = bm;
     }
     __syncthreads();
 
-    double *at = AT + warp * kProbRows * 4 * 32;
+    double *at = AT + warp * kProbRows * at_row;
     const long long n_warps = static_cast<long long>(gridDim.x) * kProbWarps;
     const long long n_iter = (A.n + kProbRows - 1) / kProbRows;
     const bool last_group = g0 + ncols >= B.n;
@@ -942,9 +941,9 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
             const long long row = A.index ? A.index[A.first + r] : (A.first + r);
             if (lane < S) {
                 const long long off = row * S + lane;
-                at[k * 128 + 4 * lane + 0] = A.cov[off];
-                at[k * 128 + 4 * lane + 1] = A.logc[off];
-                at[k * 128 + 4 * lane + 2] = -(A.lgam[off] + c_math.log_floor);
+                at[k * at_row + 4 * lane + 0] = A.cov[off];
+                at[k * at_row + 4 * lane + 1] = A.logc[off];
+                at[k * at_row + 4 * lane + 2] = -(A.lgam[off] + c_math.log_floor);
             }
         }
         __syncwarp();
@@ -992,7 +991,8 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
                     const double bc = bt[0], bl = bt[1], bm = bt[2];
 #pragma unroll
                     for (int k = 0; k < kProbRows; ++k) {
-                        const double ac = ap[k * 128], al = ap[k * 128 + 1], am = ap[k * 128 + 2];
+                        const double ac = ap[k * at_row], al = ap[k * at_row + 1],
+                                     am = ap[k * at_row + 2];
                         add_poisson_excess(s1[k], ac, am, bc, bl);
                         add_poisson_excess(s2[k], bc, bm, ac, al);
                     }
@@ -1262,7 +1262,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
     if (group < 32) group = 32;
     const long long n_groups = (b.n + group - 1) / group;
     group = ((b.n + n_groups - 1) / n_groups + 31) / 32 * 32;
-    const size_t prob_smem = sizeof(double) * (16 + 128 + kProbWarps * kProbRows * 4 * 32 + pitch * group);
+    const size_t prob_smem = sizeof(double) * (16 + 128 + kProbWarps * kProbRows * 4 * S + pitch * group);
     if (!(ctx->device < 64 && attr[ctx->device])) {
         MCG_CUDA(ctx, cudaFuncSetAttribute(dist2_kernel<0>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1298,13 +1298,14 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         oc.wmin = out.wmin - a.first;
         if (out.weights) oc.weights = out.weights - a.first * b.n;
         long long blocks = (ac.n + kProbWarps * kProbRows - 1) / (kProbWarps * kProbRows);
-        const long long cap = 3LL * ctx->sm_count * 4;
+        const long long cap = 4LL * ctx->sm_count * 4;
         if (blocks > cap) blocks = cap;
         mcg_timer_begin(ctx, T_PROB);
         for (long long g0 = 0; g0 < b.n; g0 += group) {
             const int ncols = static_cast<int>(b.n - g0 < group ? b.n - g0 : group);
             const int ncols_pad = (ncols + 31) / 32 * 32;
-            prob_kernel<<<static_cast<unsigned>(blocks), kProbThreads, prob_smem, ctx->stream>>>(
+            const size_t smem_g = prob_smem - sizeof(double) * pitch * (group - ncols);
+            prob_kernel<<<static_cast<unsigned>(blocks), kProbThreads, smem_g, ctx->stream>>>(
                 ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch, oc, d_status);
             MCG_KERNEL_CHECK(ctx);
         }
