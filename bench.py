@@ -375,10 +375,19 @@ def main():
     scan_bytes = float(np.sum((lens + 3) // 4) + n * 136 * 4 + 4 * n_seg)
     pairs = float(n) * N_BINS
     score_flops = pairs * (431 + 14 * N_SAMPLES)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    # capture of this workload (profiles/traffic.json; null when this workload was not captured)
+    try:
+        captured = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        captured = {}
+    wl_key = "%s-%d-%d-%d" % (LENGTH_KIND, N_CONTIGS, N_SAMPLES, N_BINS)
+
     def roof(kernel, bound, amount, ms, peak, unit, source, **extra):
         scale = 1e9 if unit == "GB/s" else 1e12
+        traffic = captured.get(wl_key, {}).get(kernel.split()[0])
         r = {"kernel": kernel, "bound": bound, "achieved": amount / (ms * 1e-3) / scale,
-             "peak": peak, "unit": unit, "peak_source": source, "traffic": None, "ms": ms}
+             "peak": peak, "unit": unit, "peak_source": source, "traffic": traffic, "ms": ms}
         r["frac"] = r["achieved"] / peak
         r.update(extra)
         return r
@@ -428,6 +437,9 @@ def main():
         "roofline_kernels": kernels,
         "kernel_ms": kernel_ms,
     }
+    if N_SAMPLES > 30:
+        # contigs the guarded rule-C path re-scored in the reference's operation order
+        line["config"]["redo_contigs_per_step"] = int(ctx.last_redo_count())
     if rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(blob, offsets, coverage, cen_prof, cen_cov,
                                             args.cpu_budget)

@@ -181,6 +181,13 @@ int mcg_get_assignments(mcg_ctx *ctx, int32_t *argmin, double *wmin);
 int mcg_profile(mcg_ctx *ctx, int on);
 int mcg_timings(mcg_ctx *ctx, float *ms /* [MCG_N_TIMERS] */, int64_t *launches);
 
+/* Rule C with more than 30 samples (label_prop_utils.py:308-345 on the large batches):
+ * the kernels score in the log domain and re-score, in the reference's operation order,
+ * only the contigs whose answer could depend on a Poisson product that leaves the normal
+ * double range (matching_utils.py:62-66 underflow).  This returns how many contigs the
+ * last such call re-scored (0 when the path was not taken); it synchronises the stream. */
+int mcg_last_redo_count(mcg_ctx *ctx, int64_t *count);
+
 /* ---- synthetic workloads (bench / tests) ------------------ */
 /* Fill a device-generated ASCII contig set: per-genome first-order Markov bases,
  * n_frac of positions overwritten with 'N', lower_frac of contigs lower-cased.

@@ -65,6 +65,7 @@ SIGNATURES = {
     "mcg_timings": (_int, [_vp, _vp, _vp]),
     "mcg_synth_bases": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _c.c_uint64, _dbl, _dbl, _vp]),
     "mcg_fp64_peak": (_int, [_vp, _vp]),
+    "mcg_last_redo_count": (_int, [_vp, _vp]),
 }
 
 
@@ -158,6 +159,12 @@ class Context:
         out = dict(zip(TIMER_NAMES, (float(x) for x in ms)))
         out["launches"] = int(launches.value)
         return out
+
+    def last_redo_count(self):
+        """Contigs the last S > 30 rule-C call re-scored in the reference's order."""
+        n = _c.c_int64(0)
+        self._check(self.lib.mcg_last_redo_count(self.handle, _c.byref(n)))
+        return n.value
 
     def fp64_peak(self):
         t = _c.c_double(0.0)

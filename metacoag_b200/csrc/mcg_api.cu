@@ -738,6 +738,7 @@ extern "C" int mcg_score_members(mcg_ctx *ctx, const int64_t *queries, int64_t n
     MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(int64_t) * std::max<int64_t>(nm, 1)));
     MCG_TRY(mcg_reserve(ctx, ctx->scratch[2], sizeof(int64_t) * (nseg + 1)));
     MCG_TRY(mcg_reserve(ctx, ctx->scratch[3], sizeof(double) * nq * std::max<int64_t>(nm, 1)));
+    ctx->redo_valid = false;
     MCG_TRY(mcg_reserve(ctx, ctx->scratch[4], sizeof(double) * nq * nseg));
     MCG_TRY(h2d(ctx, ctx->scratch[0].p, queries, sizeof(int64_t) * nq));
     MCG_TRY(h2d(ctx, ctx->scratch[1].p, members, sizeof(int64_t) * nm));
@@ -924,6 +925,19 @@ extern "C" int mcg_synth_bases(mcg_ctx *ctx, const int64_t *offsets, int64_t n,
                         ctx->ascii.as<uint8_t>(), n_bases));
     MCG_TRY(d2h(ctx, bases, ctx->ascii.p, static_cast<size_t>(n_bases)));
     return sync(ctx);
+}
+
+extern "C" int mcg_last_redo_count(mcg_ctx *ctx, int64_t *count) {
+    MCG_ENTER(ctx);
+    if (!count) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    *count = 0;
+    if (!ctx->redo_valid) return MCG_OK;
+    int32_t c = 0;
+    MCG_CUDA(ctx, cudaMemcpyAsync(&c, ctx->scratch[4].p, sizeof c, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *count = c;
+    return MCG_OK;
 }
 
 extern "C" int mcg_fp64_peak(mcg_ctx *ctx, double *tflops) {

@@ -497,7 +497,14 @@ __device__ __forceinline__ void tile_rows(long long *rows, double *norms, const 
 // exact zero that decides prob_product > 0) can only be reproduced by multiplying in order.
 template <bool RULE_C, bool LOGSUM>
 __global__ void __launch_bounds__(kPairThreads, 2)
-pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__ status) {
+pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__ status,
+            const int *__restrict__ n_rows_dev) {
+    // a query count that only the device knows (the redo list of the guarded rule-C path)
+    if (n_rows_dev) {
+        const long long nn = *n_rows_dev;
+        if (nn < A.n) A.n = nn;
+        if (static_cast<long long>(blockIdx.x) * kTile >= A.n) return;
+    }
     extern __shared__ __align__(16) double sm[];
     double *stage = sm;                                   // [2 stages][A, B][64][36]
     double *CA = stage + 4 * kChunkDoubles;
@@ -899,11 +906,29 @@ constexpr int kProbWarps = kProbThreads / 32;
 
 constexpr int kProbRows = 2;   // contigs per warp iteration: the bins' terms are loaded once for both
 
+// Redo list of the guarded (S > 30) path: contigs whose answer may depend on a pair whose
+// Poisson product leaves the normal range; they are re-scored by the in-order pair_kernel.
+struct RedoList {
+    int *count;           // [1]
+    long long *rows;      // table row of the contig
+    long long *pos;       // where its result goes (index into ScoreOut::argmin / wmin)
+};
+constexpr double kGuardLog = -680.0;      // log prob_cov below this: the pair is deferred
+constexpr double kGuardWeight = 295.0;    // 295 ln 10 = 679.3 < 680: no deferred pair can beat it
+constexpr int kDeferBit = 1 << 30;
+
 // bins [g0, g0 + ncols) of the B side: BT[col][pitch] = (c, log c, m) x S; warp buffers AT.
-__global__ void __launch_bounds__(kProbThreads, 4)
+//
+// GUARD (S > 30).  The log-sum form is exact only while the reference's running products stay
+// normal.  A pair whose smaller log product is below kGuardLog is *deferred*: its weight is
+// either MAX_WEIGHT or above 680 / ln 10 = 295.3, so it cannot be the argmin of a contig that
+// has a non-deferred weight below kGuardWeight.  Only contigs without such a weight go to the
+// redo list.
+template <bool GUARD>
+__global__ void __launch_bounds__(kProbThreads, GUARD ? 1 : 4)
 prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
             long long g0, int ncols, int ncols_pad, int pitch, ScoreOut out,
-            int32_t *__restrict__ status) {
+            int32_t *__restrict__ status, RedoList redo) {
     extern __shared__ __align__(16) double sm[];
     double *ET = sm;                                  // 16
     double *LT = ET + 16;                             // 128
@@ -939,11 +964,11 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
             // a missing second row repeats the first one; its results are not stored
             const long long r = r0 + k < A.n ? r0 + k : r0;
             const long long row = A.index ? A.index[A.first + r] : (A.first + r);
-            if (lane < S) {
-                const long long off = row * S + lane;
-                at[k * at_row + 4 * lane + 0] = A.cov[off];
-                at[k * at_row + 4 * lane + 1] = A.logc[off];
-                at[k * at_row + 4 * lane + 2] = -(A.lgam[off] + c_math.log_floor);
+            for (int q = lane; q < S; q += 32) {
+                const long long off = row * S + q;
+                at[k * at_row + 4 * q + 0] = A.cov[off];
+                at[k * at_row + 4 * q + 1] = A.logc[off];
+                at[k * at_row + 4 * q + 2] = -(A.lgam[off] + c_math.log_floor);
             }
         }
         __syncwarp();
@@ -951,14 +976,21 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
         int best_i[kProbRows];
         const double *d2row[kProbRows];
         double dd_next[kProbRows];
+        bool deferred[kProbRows];
 #pragma unroll
         for (int k = 0; k < kProbRows; ++k) {
             const long long r = r0 + k < A.n ? r0 + k : r0;
             best_w[k] = 0.0;
             best_i[k] = -1;
+            deferred[k] = false;
             if (g0 > 0) {   // continue from the previous bin group
                 best_w[k] = out.wmin[A.first + r];
-                best_i[k] = out.argmin[A.first + r];
+                int v = out.argmin[A.first + r];
+                if (GUARD) {   // (argmin + 1) | deferred << 30
+                    deferred[k] = (v & kDeferBit) != 0;
+                    v = (v & (kDeferBit - 1)) - 1;
+                }
+                best_i[k] = v;
             }
             d2row[k] = d2 + r * ldc + g0;
             dd_next[k] = d2row[k][lane < ncols ? lane : 0];
@@ -977,8 +1009,9 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
                 any_pc = any_pc || (log_pc[k] == log_pc[k]);   // NaN: prob_comp is exactly 0
             }
             double tsum[kProbRows];
+            bool defer_pair[kProbRows];
 #pragma unroll
-            for (int k = 0; k < kProbRows; ++k) tsum[k] = log_pc[k];
+            for (int k = 0; k < kProbRows; ++k) { tsum[k] = log_pc[k]; defer_pair[k] = false; }
             // when prob_comp is 0 for every pair of the pass the coverage terms are not needed
             if (__any_sync(0xffffffffu, any_pc)) {
                 double s1[kProbRows], s2[kProbRows];
@@ -1005,6 +1038,7 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
                     const double pmin = fma(static_cast<double>(S), c_math.log_floor,
                                             s1[k] < s2[k] ? s1[k] : s2[k]);
                     tsum[k] = log_pc[k] + pmin;   // stays NaN when prob_comp is 0
+                    if (GUARD) defer_pair[k] = live && pmin < kGuardLog && log_pc[k] == log_pc[k];
                 }
             }
 #pragma unroll
@@ -1019,7 +1053,9 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
                 }
                 const double lp = -tsum[k] * c_math.inv_ln10;
                 const double w = (valid && lp != 0.0) ? lp : MCG_MAX_WEIGHT;
-                if (live) {
+                if (GUARD && defer_pair[k]) {
+                    deferred[k] = true;   // not a candidate here; see kGuardWeight
+                } else if (live) {
                     const int bi = static_cast<int>(g0) + col;
                     if (out.weights && r0 + k < A.n)
                         out.weights[(A.first + r0 + k) * B.n + bi] = w;
@@ -1038,14 +1074,21 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
                 if (oi >= 0 && (bi < 0 || ow < bw || (ow == bw && oi < bi))) { bw = ow; bi = oi; }
             }
+            const bool def = GUARD && __any_sync(0xffffffffu, deferred[k]);
             if (lane == 0 && r0 + k < A.n) {
                 // label_prop_utils.py:342-345: None when the minimum is MAX_WEIGHT
                 const bool none = (bi < 0) || (bw == MCG_MAX_WEIGHT);
                 if (last_group) {
                     if (out.argmin) out.argmin[A.first + r0 + k] = none ? -1 : bi;
                     if (out.wmin) out.wmin[A.first + r0 + k] = none ? MCG_MAX_WEIGHT : bw;
+                    if (def && (none || !(bw < kGuardWeight))) {
+                        const int slot = atomicAdd(redo.count, 1);
+                        const long long r = r0 + k;
+                        redo.rows[slot] = A.index ? A.index[A.first + r] : (A.first + r);
+                        redo.pos[slot] = A.first + r;
+                    }
                 } else {   // carry the running minimum to the next bin group
-                    out.argmin[A.first + r0 + k] = bi;
+                    out.argmin[A.first + r0 + k] = GUARD ? ((bi + 1) | (def ? kDeferBit : 0)) : bi;
                     out.wmin[A.first + r0 + k] = bw;
                 }
             }
@@ -1177,7 +1220,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 }  // namespace
 
 // ---- launchers -------------------------------------------------------------------------------
-typedef void (*pair_fn)(ScoreSide, ScoreSide, int, ScoreOut, int32_t *);
+typedef void (*pair_fn)(ScoreSide, ScoreSide, int, ScoreOut, int32_t *, const int *);
 static pair_fn pair_variant(bool rule_c, bool logsum) {
     if (rule_c) return logsum ? pair_kernel<true, true> : pair_kernel<true, false>;
     return logsum ? pair_kernel<false, true> : pair_kernel<false, false>;
@@ -1249,27 +1292,55 @@ int mcg_k_cov_terms(mcg_ctx *ctx, double *d_cov, double *d_logc, double *d_lgam,
     return MCG_OK;
 }
 
+// argmin / wmin of the re-scored contigs go back to their places.
+__global__ void scatter_redo_kernel(const int *__restrict__ count, const long long *__restrict__ pos,
+                                    const int32_t *__restrict__ arg, const double *__restrict__ w,
+                                    int32_t *__restrict__ out_arg, double *__restrict__ out_w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    out_arg[pos[i]] = arg[i];
+    out_w[pos[i]] = w[i];
+}
+
+static size_t prob_smem_bytes(int S, long long group) {
+    return sizeof(double) * (16 + 128 + kProbWarps * kProbRows * 4 * S + bin_pitch(S) * group);
+}
+
+// Can the two-kernel rule-C path take S samples at all (one warp of bins per group)?
+static bool split_fits(int S) { return prob_smem_bytes(S, 32) <= 200 * 1024; }
+
 // The two-kernel rule-C path over row chunks of the A side (the d^2 scratch is bounded).
+// S <= 30: the log-sum form is exact for every pair.  S > 30: prob_kernel<true> defers the
+// pairs whose Poisson product may leave the normal range and lists the contigs whose answer
+// could depend on one; pair_kernel re-scores those in the reference's operation order.
 static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int S,
                         const ScoreOut &out, int32_t *d_status) {
     static bool attr[64] = {};
+    const bool guard = S > 30;
     const long long b_tiles = (b.n + kTile - 1) / kTile;
     const long long ldc = b_tiles * kTile;
-    // bins per shared-memory group of prob_kernel (<= 44 KB of terms), whole warps of columns
+    // bins per shared-memory group of prob_kernel, whole warps of columns: S <= 30 keeps the
+    // terms under 56 KB (4 CTAs per SM); larger S takes up to ~100 KB (2 CTAs per SM), or one
+    // warp of bins when even that does not fit
     const int pitch = bin_pitch(S);
-    long long group = (56 * 1024) / (sizeof(double) * pitch);
+    const long long fixed = static_cast<long long>(prob_smem_bytes(S, 0));
+    long long budget = guard ? 104 * 1024 - fixed : 56 * 1024;
+    long long group = budget > 0 ? budget / static_cast<long long>(sizeof(double) * pitch) : 0;
     group = (group / 32) * 32;
     if (group < 32) group = 32;
     const long long n_groups = (b.n + group - 1) / group;
     group = ((b.n + n_groups - 1) / n_groups + 31) / 32 * 32;
-    const size_t prob_smem = sizeof(double) * (16 + 128 + kProbWarps * kProbRows * 4 * S + pitch * group);
+    const size_t prob_smem = prob_smem_bytes(S, group);
     if (!(ctx->device < 64 && attr[ctx->device])) {
         MCG_CUDA(ctx, cudaFuncSetAttribute(dist2_kernel<0>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(kDistSmem)));
-        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel,
+        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            96 * 1024));
+        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
         if (ctx->device < 64) attr[ctx->device] = true;
     }
     // rows per chunk: <= 512 MiB of scratch, whole tiles
@@ -1280,6 +1351,26 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
                                 kTile * kTile;
     MCG_TRY(mcg_reserve(ctx, ctx->scratch[5], sizeof(double) * need_rows * ldc));
     double *d2 = ctx->scratch[5].as<double>();
+    RedoList redo = {nullptr, nullptr, nullptr};
+    int32_t *redo_arg = nullptr;
+    double *redo_w = nullptr;
+    if (guard) {
+        // [count | pad] [rows a.n] [pos a.n] [wmin a.n] [argmin a.n]
+        const size_t bytes = 16 + static_cast<size_t>(a.n) * (8 + 8 + 8 + 4);
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[4], bytes));
+        char *base = ctx->scratch[4].as<char>();
+        redo.count = reinterpret_cast<int *>(base);
+        redo.rows = reinterpret_cast<long long *>(base + 16);
+        redo.pos = redo.rows + a.n;
+        redo_w = reinterpret_cast<double *>(redo.pos + a.n);
+        redo_arg = reinterpret_cast<int32_t *>(redo_w + a.n);
+        MCG_CUDA(ctx, cudaMemsetAsync(redo.count, 0, 16, ctx->stream));
+    }
+    ctx->redo_valid = guard;
+    ScoreOut shifted = out;   // outputs are indexed by (first + r): shift them back
+    shifted.argmin = out.argmin - a.first;
+    shifted.wmin = out.wmin - a.first;
+    if (out.weights) shifted.weights = out.weights - a.first * b.n;
     for (long long r0 = 0; r0 < a.n; r0 += rows_per_chunk) {
         ScoreSide ac = a;
         ac.first = a.first + r0;
@@ -1293,10 +1384,6 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc);
         mcg_timer_end(ctx, T_DIST);
         MCG_KERNEL_CHECK(ctx);
-        ScoreOut oc = out;   // outputs are indexed by (first + r): shift them back to the chunk
-        oc.argmin = out.argmin - a.first;
-        oc.wmin = out.wmin - a.first;
-        if (out.weights) oc.weights = out.weights - a.first * b.n;
         long long blocks = (ac.n + kProbWarps * kProbRows - 1) / (kProbWarps * kProbRows);
         const long long cap = 4LL * ctx->sm_count * 4;
         if (blocks > cap) blocks = cap;
@@ -1305,10 +1392,35 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
             const int ncols = static_cast<int>(b.n - g0 < group ? b.n - g0 : group);
             const int ncols_pad = (ncols + 31) / 32 * 32;
             const size_t smem_g = prob_smem - sizeof(double) * pitch * (group - ncols);
-            prob_kernel<<<static_cast<unsigned>(blocks), kProbThreads, smem_g, ctx->stream>>>(
-                ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch, oc, d_status);
+            if (guard)
+                prob_kernel<true><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
+                                    ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch,
+                                                   shifted, d_status, redo);
+            else
+                prob_kernel<false><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
+                                     ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch,
+                                                    shifted, d_status, redo);
             MCG_KERNEL_CHECK(ctx);
         }
+        // (the timer holds one interval: with S > 30 it closes after the redo pass below)
+        if (!(guard && r0 + rows_per_chunk >= a.n)) mcg_timer_end(ctx, T_PROB);
+    }
+    if (guard) {
+        // the listed contigs again, in the reference's operation order; the grid covers the
+        // worst case and the CTAs beyond the device-side count leave at once
+        ScoreSide ar = a;
+        ar.index = reinterpret_cast<const int64_t *>(redo.rows);
+        ar.first = 0;
+        ScoreOut ro;
+        ro.argmin = redo_arg;
+        ro.wmin = redo_w;
+        const long long a_tiles = (a.n + kTile - 1) / kTile;
+        pair_variant(true, false)<<<dim3(static_cast<unsigned>(a_tiles), 1, 1), kPairThreads,
+                                    kPairSmem, ctx->stream>>>(ar, b, S, ro, d_status, redo.count);
+        MCG_KERNEL_CHECK(ctx);
+        scatter_redo_kernel<<<blocks_for(a.n, 256), 256, 0, ctx->stream>>>(
+            redo.count, redo.pos, redo_arg, redo_w, shifted.argmin, shifted.wmin);
+        MCG_KERNEL_CHECK(ctx);
         mcg_timer_end(ctx, T_PROB);
     }
     return MCG_OK;
@@ -1335,6 +1447,7 @@ int mcg_k_normalise_norms(mcg_ctx *ctx, const uint32_t *d_counts, const ContigMe
 int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samples,
                 const ScoreOut &out, int32_t *d_status) {
     MCG_TRY(ensure_gauss(ctx));
+    ctx->redo_valid = false;
     if (a.n == 0) return MCG_OK;
     const bool rule_c = out.argmin != nullptr || out.wmin != nullptr || out.weights != nullptr;
     const long long a_tiles = (a.n + kTile - 1) / kTile;
@@ -1344,7 +1457,9 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
     const bool logsum = n_samples <= 30;
     // big rule-C batches: distance GEMM + probability kernel (argmin/wmin are needed to
     // carry the running minimum when the bins do not fit one shared-memory group)
-    if (rule_c && logsum && a.n >= 2048 && out.argmin && out.wmin)
+    // (S > 30: only without the weight matrix -- deferred pairs have no exact weight there)
+    if (rule_c && a.n >= 2048 && out.argmin && out.wmin &&
+        (logsum || (!out.weights && split_fits(n_samples))))
         return split_rule_c(ctx, a, b, n_samples, out, d_status);
     if (out.dist) {
         pair_distance_kernel<<<blocks_for(a.n * b.n, 128), 128, 0, ctx->stream>>>(a, b, out.dist);
@@ -1359,7 +1474,7 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
         grid.y = static_cast<unsigned>(gy);
     }
     pair_variant(rule_c, logsum)<<<grid, kPairThreads, kPairSmem, ctx->stream>>>(
-        a, b, n_samples, out, d_status);
+        a, b, n_samples, out, d_status, nullptr);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }

@@ -287,6 +287,45 @@ def test_rule_c_vs_oracle(ctx, S, B, n):
         assert_close(ctx.score_members(q, members, seg, rule), want)
 
 
+@pytest.mark.parametrize("S,B,n,orphans", [(33, 70, 2100, False), (50, 300, 2300, False),
+                                           (50, 300, 2300, True), (100, 40, 2100, True),
+                                           (64, 520, 2050, True)])
+def test_rule_c_guarded_path_vs_oracle(ctx, S, B, n, orphans):
+    """S > 30 on the two-kernel path: log-domain scoring with deferred pairs, and the redo of
+    the contigs that have no weight below 295 (label_prop_utils.py:308-345 must come out the
+    same: first argmin, None, weights).  `orphans` gives every third contig coverages that
+    match no bin, which forces the redo path."""
+    asm = synth.make_assembly(seed=300 + S, n_genomes=B, n_contigs=n, n_samples=S,
+                              length_kind="mixed", with_graph=False, with_markers=False)
+    _, prof = oracle.count_kmers_batch(asm.blob, asm.offsets, nthreads=0)
+    cov = asm.coverage.copy()
+    if orphans:
+        rng = np.random.default_rng(S)
+        rows = np.arange(0, n, 3)
+        cov[rows] = np.maximum(np.round(rng.lognormal(3.0, 1.5, (rows.size, S)), 4), 1e-4)
+        cov[rows[::4], : S // 2] = 1e-4      # long runs of clamped zeros: terms ~ 1, "sticking"
+    members, seg = [], [0]
+    for g in range(B):
+        ids = np.flatnonzero(asm.genome_of == g)[:6]
+        if ids.size == 0:
+            ids = np.array([g % n])
+        members.extend(ids.tolist())
+        seg.append(len(members))
+    cen_prof = oracle.segment_mean(prof, members, seg)
+    cen_cov = oracle.segment_mean(cov, members, seg)
+    want_arg, want_w, _ = oracle.score_centroids(prof, cov, cen_prof, cen_cov, nthreads=0)
+    ctx.set_profiles(prof)
+    ctx.load_coverage(cov)
+    arg, w = ctx.score_centroids(cen_prof=cen_prof, cen_cov=cen_cov)[:2]
+    redo = ctx.last_redo_count()
+    assert np.array_equal(arg, want_arg)
+    assert_close(w, want_w)
+    assert 0 <= redo <= n
+    if orphans:
+        assert redo > 0          # the in-order path ran ...
+    assert redo < n              # ... and the log-domain path decided the rest
+
+
 def test_fused_call_matches_staged(ctx):
     asm = synth.make_assembly(seed=9, n_genomes=12, n_contigs=500, n_samples=5,
                               with_graph=False, with_markers=False)
