@@ -85,6 +85,23 @@ int mcg_tetramer_scan(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets
 int mcg_load_contigs(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n,
                      int encoding);
 int mcg_scan(mcg_ctx *ctx);
+/* ASCII loads of 16 MB and more are split between the copy engine (ASCII chunks, packed to
+ * 2 bits by a kernel) and `threads` host threads that pack chunks themselves so that only
+ * a quarter of their bytes cross the link; the two sides work towards each other, so the
+ * split follows their measured speeds, and the packed store is bit-identical either way.
+ * threads = 0 turns the host side off; -1 (default) takes MCG_HOST_PACK_THREADS from the
+ * environment, else the number of hardware threads.  (Replaces the per-sequence pickling
+ * to a worker pool of feature_utils.py:97-104.) */
+int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads);
+/* The host-side packer on its own: ASCII contigs -> the MCG_ENC_2BIT layout described above
+ * (packed has 16 * sum_c ceil(len_c / 64) bytes).  Pure host code, no device needed.
+ * level -1 = best SIMD variant of this CPU, 0 scalar, 1 AVX2, 2 AVX-512BW, 3 AVX2 with a
+ * masked 512-bit tail; a level the CPU lacks falls back to the next lower one. */
+int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, int64_t n, uint8_t *packed,
+                       int level);
+/* Last ASCII load: stats[0] bytes copied host->device for the bases, [1] bases packed by
+ * host threads, [2] bases packed by the kernel, [3] host threads used. */
+int mcg_ingest_stats(mcg_ctx *ctx, int64_t stats[4]);
 int mcg_get_profiles(mcg_ctx *ctx, int64_t first, int64_t n, uint32_t *counts, double *freqs);
 /* Contig table from host profiles (the dict the Python API carries around). */
 int mcg_set_profiles(mcg_ctx *ctx, const double *prof /* [n,136] */, int64_t n);

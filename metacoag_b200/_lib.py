@@ -66,6 +66,9 @@ SIGNATURES = {
     "mcg_synth_bases": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _c.c_uint64, _dbl, _dbl, _vp]),
     "mcg_fp64_peak": (_int, [_vp, _vp]),
     "mcg_last_redo_count": (_int, [_vp, _vp]),
+    "mcg_set_host_pack_threads": (_int, [_vp, _int]),
+    "mcg_ingest_stats": (_int, [_vp, _vp]),
+    "mcg_pack_2bit_host": (_int, [_vp, _vp, _i64, _vp, _int]),
 }
 
 
@@ -106,6 +109,19 @@ def _arr(a, dtype, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def pack_2bit_host(bases, offsets, level=-1):
+    """ASCII contigs -> MCG_ENC_2BIT bytes with the library's host packer (no device)."""
+    bases = _arr(bases, np.uint8)
+    offsets = _arr(offsets, np.int64)
+    n = offsets.shape[0] - 1
+    nbytes = int(np.sum(16 * ((np.diff(offsets) + 63) // 64)))
+    out = np.zeros(nbytes, dtype=np.uint8)
+    rc = load_library().mcg_pack_2bit_host(_ptr(bases), _ptr(offsets), n, _ptr(out), int(level))
+    if rc != OK:
+        raise McgError(rc, "mcg_pack_2bit_host failed")
+    return out
 
 
 class Context:
@@ -159,6 +175,17 @@ class Context:
         out = dict(zip(TIMER_NAMES, (float(x) for x in ms)))
         out["launches"] = int(launches.value)
         return out
+
+    def set_host_pack_threads(self, threads):
+        """Host threads that pack ASCII chunks during a load (0 = copy engine only)."""
+        self._check(self.lib.mcg_set_host_pack_threads(self.handle, int(threads)))
+
+    def ingest_stats(self):
+        """Last ASCII load: h2d bytes of the bases, host-packed / kernel-packed bases, threads."""
+        st = np.zeros(4, dtype=np.int64)
+        self._check(self.lib.mcg_ingest_stats(self.handle, _ptr(st)))
+        return {"h2d_bytes": int(st[0]), "host_packed_bases": int(st[1]),
+                "gpu_packed_bases": int(st[2]), "host_threads": int(st[3])}
 
     def last_redo_count(self):
         """Contigs the last S > 30 rule-C call re-scored in the reference's order."""

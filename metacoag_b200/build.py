@@ -15,6 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcg_b200.so")
 SOURCES = ["mcg_api.cu", "mcg_scan.cu", "mcg_score.cu", "mcg_frontier.cu"]
+HOST_SOURCES = ["mcg_hostpack.cpp"]
 HEADERS = [os.path.join(CSRC, "mcg_internal.cuh"), os.path.join(ROOT, "include", "mcg_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -33,7 +34,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HOST_SOURCES] + HEADERS
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -49,6 +50,16 @@ def build_library(force=False, verbose=False):
                                 os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    # the host half of the ingest (AVX2 / AVX-512 variants behind a run-time check) goes
+    # through g++ directly
+    for src in HOST_SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cpp", ".o"))
+        cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-Wall", "-c",
+               os.path.join(CSRC, src), "-o", obj]
+        if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
         objs.append(obj)

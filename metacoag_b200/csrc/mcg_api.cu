@@ -1,6 +1,9 @@
 // C ABI of libmcg_b200.so (include/mcg_b200.h): context, staging and the host-facing entry
 // points.  The kernels live in mcg_scan.cu, mcg_score.cu and mcg_frontier.cu.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "mcg_internal.cuh"
@@ -146,6 +149,8 @@ extern "C" mcg_ctx *mcg_create(int device) {
     }
     ctx->stream = ctx->own_stream;
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->copy2_done, cudaEventDisableTiming);
     for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->copy_start, cudaEventDisableTiming);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i) cudaEventCreate(&ctx->ev[i]);
@@ -171,6 +176,9 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
     for (DevBuf &b : ctx->scratch)
         if (b.p) cudaFree(b.p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_pack) cudaFreeHost(ctx->pinned_pack);
+    if (ctx->copy2_done) cudaEventDestroy(ctx->copy2_done);
+    if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 4; ++i)
@@ -255,6 +263,201 @@ static int build_layout(mcg_ctx *ctx, const int64_t *offsets, int64_t n,
     return MCG_OK;
 }
 
+// ---- ASCII ingest: copy engine + GPU pack kernel from the front, host threads + 4x smaller
+// copies from the back ------------------------------------------------------------------------
+extern "C" void mcg_hostpack_range(const uint8_t *bases, const int64_t *offsets, int64_t c0,
+                                   int64_t c1, const void *first_word, int64_t word_stride_bytes,
+                                   uint8_t *packed, int level);
+
+static int host_pack_threads(mcg_ctx *ctx, int64_t n_bases) {
+    if (n_bases < (16 << 20)) return 0;   // small loads: the plain upload is already short
+    int t = ctx->host_pack_threads;
+    if (t < 0) {
+        const char *env = getenv("MCG_HOST_PACK_THREADS");
+        if (env && *env) t = atoi(env);
+        else t = static_cast<int>(std::thread::hardware_concurrency());   // the caller only polls
+    }
+    return t < 0 ? 0 : (t > 256 ? 256 : t);
+}
+
+// The contig blob is cut into chunks of whole contigs (~1 MB of bases).  The calling thread
+// feeds the copy engine with runs of ASCII chunks taken from the front (~8 MB per copy, at
+// most two in flight, each followed by its pack kernel on the compute stream); `threads` host
+// threads take single chunks from the back, pack them into pinned memory (mcg_hostpack.cpp)
+// and the calling thread copies the packed result, adjacent chunks in one copy.  Both sides
+// stop when they meet, so the split follows the measured speeds of the link and of the host,
+// and the small host chunks keep the tail (workers finishing while the link idles) short.
+// Output is the same packed store either way.
+static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n,
+                        const std::vector<ContigMeta> &meta, int64_t n_words) {
+    if (n == 0) return MCG_OK;
+    const int64_t n_bases = offsets[n];
+    const int threads = host_pack_threads(ctx, n_bases);
+    struct Chunk { int64_t c0, c1; };
+    std::vector<Chunk> chunks;
+    const int64_t chunk_bytes = threads > 0 ? (1 << 20) : (32 << 20);
+    const int64_t copy_bytes = threads > 0 ? (8 << 20) : (32 << 20);   // ASCII bytes per copy
+    const int64_t packed_copy_words = (1 << 20) / 4;   // packed copies are batched to >= 1 MB
+    for (int64_t c0 = 0; c0 < n;) {
+        int64_t c1 = c0;
+        while (c1 < n && offsets[c1] - offsets[c0] < chunk_bytes) ++c1;
+        chunks.push_back({c0, c1});
+        c0 = c1;
+    }
+    const int64_t n_chunks = static_cast<int64_t>(chunks.size());
+    if (n_chunks >= 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many contig chunks");
+    uint8_t *stage = nullptr;
+    if (threads > 0) {
+        const size_t need = sizeof(uint32_t) * static_cast<size_t>(n_words);
+        if (need > ctx->pinned_pack_cap) {
+            if (ctx->pinned_pack) {
+                cudaStreamSynchronize(ctx->copy_stream2);
+                cudaFreeHost(ctx->pinned_pack);
+                ctx->pinned_pack = nullptr;
+                ctx->pinned_pack_cap = 0;
+            }
+            if (cudaMallocHost(&ctx->pinned_pack, need) != cudaSuccess)
+                return mcg_fail(ctx, MCG_ERR_NOMEM, "cudaMallocHost(%zu) failed", need);
+            ctx->pinned_pack_cap = need;
+        }
+        stage = static_cast<uint8_t *>(ctx->pinned_pack);
+    }
+    MCG_CUDA(ctx, cudaEventRecord(ctx->copy_start, ctx->stream));
+    MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_start, 0));
+    MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream2, ctx->copy_start, 0));
+
+    // Unclaimed chunks are [front, end): one 64-bit word, claimed by compare-and-swap from
+    // either side, so that the polling caller never holds a lock the workers need.
+    std::atomic<uint64_t> range(static_cast<uint64_t>(n_chunks));   // front << 32 | end
+    std::vector<std::atomic<int64_t>> ready(static_cast<size_t>(n_chunks));   // packed chunks, in
+    for (auto &r : ready) r.store(-1, std::memory_order_relaxed);             // completion order
+    std::atomic<int64_t> ready_tail(0);
+    std::atomic<int> workers_left(threads);
+    auto claim_back = [&]() -> int64_t {
+        uint64_t v = range.load(std::memory_order_relaxed);
+        for (;;) {
+            const uint64_t f = v >> 32, e = v & 0xffffffffu;
+            if (f >= e) return -1;
+            if (range.compare_exchange_weak(v, (f << 32) | (e - 1), std::memory_order_acq_rel))
+                return static_cast<int64_t>(e - 1);
+        }
+    };
+    auto claim_front_run = [&](Chunk *run) -> bool {
+        uint64_t v = range.load(std::memory_order_relaxed);
+        for (;;) {
+            const uint64_t f = v >> 32, e = v & 0xffffffffu;
+            if (f >= e) return false;
+            uint64_t k = f;
+            run->c0 = chunks[f].c0;
+            do run->c1 = chunks[k++].c1;
+            while (k < e && offsets[run->c1] - offsets[run->c0] < copy_bytes);
+            if (range.compare_exchange_weak(v, (k << 32) | e, std::memory_order_acq_rel)) return true;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const int64_t k = claim_back();
+                if (k < 0) break;
+                mcg_hostpack_range(bases, offsets, chunks[k].c0, chunks[k].c1, &meta[0].pk_word,
+                                   sizeof(ContigMeta), stage, -1);
+                ready[ready_tail.fetch_add(1, std::memory_order_relaxed)].store(
+                    k, std::memory_order_release);
+            }
+            workers_left.fetch_sub(1, std::memory_order_release);
+        });
+
+    int rc = MCG_OK;
+    int64_t h2d_bytes = 0, host_bases = 0, gpu_bases = 0;
+    int inflight[2] = {-1, -1};          // copy_ev slots of the ASCII runs on the wire
+    int slot = 0;
+    auto word_range = [&](const Chunk &ch, int64_t *w0, int64_t *w1) {
+        *w0 = meta[ch.c0].pk_word;
+        *w1 = ch.c1 < n ? meta[ch.c1].pk_word : n_words;
+    };
+    // host-packed chunks complete roughly from the back; they are copied as runs that end at
+    // `up_hi`, the highest chunk not yet copied
+    std::vector<char> packed_done(static_cast<size_t>(n_chunks), 0);
+    int64_t ready_head = 0, up_hi = n_chunks - 1;
+    for (bool done = false; !done && rc == MCG_OK;) {
+        bool progressed = false;
+        for (int &f : inflight)   // retire ASCII copies that have left
+            if (f >= 0 && cudaEventQuery(ctx->copy_ev[f]) != cudaErrorNotReady) { f = -1; progressed = true; }
+        for (int &f : inflight) {   // next ASCII run from the front
+            if (f >= 0) continue;
+            Chunk ch;
+            if (!claim_front_run(&ch)) break;
+            const size_t bytes = static_cast<size_t>(offsets[ch.c1] - offsets[ch.c0]);
+            cudaError_t e = cudaSuccess;
+            if (bytes)
+                e = cudaMemcpyAsync(ctx->ascii.as<uint8_t>() + offsets[ch.c0], bases + offsets[ch.c0],
+                                    bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0);
+            if (e != cudaSuccess) {
+                rc = mcg_fail(ctx, MCG_ERR_CUDA, "contig upload failed: %s", cudaGetErrorString(e));
+                break;
+            }
+            int64_t w0, w1;
+            word_range(ch, &w0, &w1);
+            rc = mcg_k_pack_ascii(ctx, ctx->ascii.as<uint8_t>(), ctx->offsets.as<int64_t>(),
+                                  ctx->meta.as<ContigMeta>(), n, w0, w1 - w0,
+                                  ctx->packed.as<uint32_t>());
+            if (rc != MCG_OK) break;
+            f = slot;
+            slot = (slot + 1) & 3;
+            h2d_bytes += static_cast<int64_t>(bytes);
+            gpu_bases += static_cast<int64_t>(bytes);
+            progressed = true;
+        }
+        // everything claimed and every worker gone: the remaining packed chunks are final
+        const bool finishing = workers_left.load(std::memory_order_acquire) == 0 &&
+                               (range.load(std::memory_order_acquire) >> 32) >=
+                                   (range.load(std::memory_order_acquire) & 0xffffffffu);
+        while (ready_head < n_chunks) {
+            const int64_t k = ready[ready_head].load(std::memory_order_acquire);
+            if (k < 0) break;
+            packed_done[k] = 1;
+            ++ready_head;
+        }
+        while (rc == MCG_OK && up_hi >= 0 && packed_done[up_hi]) {
+            int64_t lo = up_hi;
+            while (lo > 0 && packed_done[lo - 1]) --lo;
+            const Chunk run = {chunks[lo].c0, chunks[up_hi].c1};
+            int64_t w0, w1;
+            word_range(run, &w0, &w1);
+            if (!finishing && w1 - w0 < packed_copy_words) break;   // let the run grow
+            const size_t bytes = sizeof(uint32_t) * static_cast<size_t>(w1 - w0);
+            if (bytes) {
+                cudaError_t e = cudaMemcpyAsync(ctx->packed.as<uint32_t>() + w0, stage + 4 * w0, bytes,
+                                                cudaMemcpyHostToDevice, ctx->copy_stream2);
+                if (e != cudaSuccess)
+                    rc = mcg_fail(ctx, MCG_ERR_CUDA, "packed upload failed: %s", cudaGetErrorString(e));
+            }
+            h2d_bytes += static_cast<int64_t>(bytes);
+            host_bases += offsets[run.c1] - offsets[run.c0];
+            up_hi = lo - 1;
+            progressed = true;
+        }
+        // done: nothing left to claim, workers gone, and every packed chunk handed over (the
+        // chunks below up_hi that are not packed_done went to the copy engine as ASCII)
+        done = finishing && ready_head == ready_tail.load(std::memory_order_acquire) &&
+               (up_hi < 0 || !packed_done[up_hi]);
+        if (!progressed && !done) std::this_thread::yield();
+    }
+    if (rc != MCG_OK) range.store(0);   // let the workers run out of chunks
+    for (std::thread &t : pool) t.join();
+    if (rc != MCG_OK) return rc;
+    MCG_CUDA(ctx, cudaEventRecord(ctx->copy2_done, ctx->copy_stream2));
+    MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy2_done, 0));
+    ctx->ingest_stats[0] = h2d_bytes;
+    ctx->ingest_stats[1] = host_bases;
+    ctx->ingest_stats[2] = gpu_bases;
+    ctx->ingest_stats[3] = threads;
+    return MCG_OK;
+}
+
 static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
                                int64_t n, int encoding) {
     if (n < 0 || (!offsets && n > 0)) return mcg_fail(ctx, MCG_ERR_ARG, "bad contig arguments");
@@ -281,31 +484,7 @@ static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t
             MCG_TRY(mcg_reserve(ctx, ctx->ascii, static_cast<size_t>(n_bases) + 256));
             MCG_TRY(mcg_reserve(ctx, ctx->offsets, sizeof(int64_t) * (n + 1)));
             MCG_TRY(h2d(ctx, ctx->offsets.p, offsets, sizeof(int64_t) * (n + 1)));
-            // The bases go up in chunks of whole contigs (~32 MB) on a second stream; the
-            // pack kernel of chunk i runs while chunk i+1 is still on the wire.
-            MCG_CUDA(ctx, cudaEventRecord(ctx->copy_start, ctx->stream));
-            MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_start, 0));
-            const int64_t chunk_bytes = 32 << 20;
-            int64_t c0 = 0;
-            int slot = 0;
-            while (c0 < n) {
-                int64_t c1 = c0;
-                while (c1 < n && offsets[c1] - offsets[c0] < chunk_bytes) ++c1;
-                const size_t bytes = static_cast<size_t>(offsets[c1] - offsets[c0]);
-                if (bytes)
-                    MCG_CUDA(ctx, cudaMemcpyAsync(ctx->ascii.as<uint8_t>() + offsets[c0],
-                                                  bases + offsets[c0], bytes,
-                                                  cudaMemcpyHostToDevice, ctx->copy_stream));
-                MCG_CUDA(ctx, cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream));
-                MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0));
-                const int64_t w0 = meta[c0].pk_word;
-                const int64_t w1 = c1 < n ? meta[c1].pk_word : n_words;
-                MCG_TRY(mcg_k_pack_ascii(ctx, ctx->ascii.as<uint8_t>(), ctx->offsets.as<int64_t>(),
-                                         ctx->meta.as<ContigMeta>(), n, w0, w1 - w0,
-                                         ctx->packed.as<uint32_t>()));
-                slot = (slot + 1) & 3;
-                c0 = c1;
-            }
+            MCG_TRY(upload_ascii(ctx, bases, offsets, n, meta, n_words));
         } else {
             MCG_TRY(h2d(ctx, ctx->packed.p, bases, sizeof(uint32_t) * n_words));
         }
@@ -925,6 +1104,33 @@ extern "C" int mcg_synth_bases(mcg_ctx *ctx, const int64_t *offsets, int64_t n,
                         ctx->ascii.as<uint8_t>(), n_bases));
     MCG_TRY(d2h(ctx, bases, ctx->ascii.p, static_cast<size_t>(n_bases)));
     return sync(ctx);
+}
+
+extern "C" int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, int64_t n,
+                                  uint8_t *packed, int level) {
+    if (n < 0 || (n > 0 && (!offsets || !packed))) return MCG_ERR_ARG;
+    std::vector<int64_t> first(static_cast<size_t>(n) + 1, 0);
+    for (int64_t c = 0; c < n; ++c) {
+        const int64_t len = offsets[c + 1] - offsets[c];
+        if (len < 0) return MCG_ERR_ARG;
+        first[c + 1] = first[c] + 4 * ((len + 63) / 64);
+    }
+    if (n > 0 && offsets[n] > offsets[0] && !bases) return MCG_ERR_ARG;
+    mcg_hostpack_range(bases, offsets, 0, n, first.data(), sizeof(int64_t), packed, level);
+    return MCG_OK;
+}
+
+extern "C" int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads) {
+    MCG_ENTER(ctx);
+    ctx->host_pack_threads = threads;
+    return MCG_OK;
+}
+
+extern "C" int mcg_ingest_stats(mcg_ctx *ctx, int64_t stats[4]) {
+    MCG_ENTER(ctx);
+    if (!stats) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    for (int i = 0; i < 4; ++i) stats[i] = ctx->ingest_stats[i];
+    return MCG_OK;
 }
 
 extern "C" int mcg_last_redo_count(mcg_ctx *ctx, int64_t *count) {

@@ -1,0 +1,152 @@
+// Host half of the contig ingest: ASCII bases -> the 2-bit packed store layout.
+//
+//   reference: feature_utils.py:18-35 (nt_bits / mer2bits): A0 C1 G2 T3 and ANY other
+//   byte 0 (lower case and N included, feature_utils.py:21).
+//
+// Same output, bit for bit, as pack_ascii_kernel (mcg_scan.cu): base i of a contig in bits
+// [2(i%16), +2) of 32-bit word i/16, every contig padded with zeros to a multiple of 64 bases
+// (16 bytes).  This is format conversion for the PCIe link, not part of the scored
+// arithmetic: mcg_load_contigs splits the contig blob between the copy engine (ASCII chunks,
+// packed by the GPU kernel) and these routines (host threads pack, the 4x smaller result is
+// copied), so that an upload costs max(link, host) instead of 8 bits per base on the link.
+//
+// Compiled by g++ (not nvcc): AVX-512BW / AVX2 + BMI2 variants picked at run time, scalar
+// otherwise.
+#include <immintrin.h>
+
+#include <cstdint>
+#include <cstring>
+
+namespace {
+
+// The packed block of 64 bases.  The output is written once and next read by the copy engine:
+// a non-temporal store (when the block is 16-byte aligned, as it is in the pinned staging
+// buffer) saves the read-for-ownership of the line, and the upload is bound by host DRAM
+// traffic once enough threads pack.
+__attribute__((target("sse2"))) inline void store16(uint8_t *dst, uint64_t w0, uint64_t w1) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst),
+                         _mm_set_epi64x(static_cast<long long>(w1), static_cast<long long>(w0)));
+    } else {
+        memcpy(dst, &w0, 8);
+        memcpy(dst + 8, &w1, 8);
+    }
+}
+
+// 64 bases (mask = which of them exist) -> 16 bytes.
+__attribute__((target("avx512bw,avx512vl,bmi2"))) inline void block_avx512(const uint8_t *src,
+                                                                            uint64_t mask,
+                                                                            uint8_t *dst) {
+    const __m512i v = _mm512_maskz_loadu_epi8(mask, src);   // masked-off bytes are not touched
+    const uint64_t mc = _mm512_cmpeq_epi8_mask(v, _mm512_set1_epi8('C'));
+    const uint64_t mg = _mm512_cmpeq_epi8_mask(v, _mm512_set1_epi8('G'));
+    const uint64_t mt = _mm512_cmpeq_epi8_mask(v, _mm512_set1_epi8('T'));
+    const uint64_t lo = mc | mt, hi = mg | mt;
+    const uint64_t w0 = _pdep_u64(lo, 0x5555555555555555ull) | _pdep_u64(hi, 0xAAAAAAAAAAAAAAAAull);
+    const uint64_t w1 = _pdep_u64(lo >> 32, 0x5555555555555555ull) |
+                        _pdep_u64(hi >> 32, 0xAAAAAAAAAAAAAAAAull);
+    store16(dst, w0, w1);
+}
+
+__attribute__((target("avx512bw,avx512vl,bmi2"))) void contig_avx512(const uint8_t *src,
+                                                                      int64_t len, uint8_t *dst) {
+    const int64_t full = len / 64;
+    for (int64_t i = 0; i < full; ++i) block_avx512(src + 64 * i, ~0ull, dst + 16 * i);
+    const int rem = static_cast<int>(len - 64 * full);
+    if (rem) block_avx512(src + 64 * full, (1ull << rem) - 1ull, dst + 16 * full);
+}
+
+__attribute__((target("avx2,bmi2"))) inline uint64_t half_avx2(const uint8_t *src) {
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src));
+    const uint32_t mc = _mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('C')));
+    const uint32_t mg = _mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('G')));
+    const uint32_t mt = _mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('T')));
+    const uint64_t lo = mc | mt, hi = mg | mt;
+    return _pdep_u64(lo, 0x5555555555555555ull) | _pdep_u64(hi, 0xAAAAAAAAAAAAAAAAull);
+}
+
+inline uint32_t code_of(uint8_t c) { return c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u; }
+
+void tail_scalar(const uint8_t *src, int64_t len, uint8_t *dst) {
+    // len < 64 bases into one zero-padded 16-byte block
+    uint64_t w[2] = {0, 0};
+    for (int64_t i = 0; i < len; ++i) w[i >> 5] |= static_cast<uint64_t>(code_of(src[i])) << (2 * (i & 31));
+    memcpy(dst, w, 16);
+}
+
+__attribute__((target("avx2,bmi2"))) void contig_avx2(const uint8_t *src, int64_t len,
+                                                      uint8_t *dst) {
+    const int64_t full = len / 64;
+    for (int64_t i = 0; i < full; ++i) {
+        const uint64_t w0 = half_avx2(src + 64 * i), w1 = half_avx2(src + 64 * i + 32);
+        store16(dst + 16 * i, w0, w1);
+    }
+    if (len > 64 * full) tail_scalar(src + 64 * full, len - 64 * full, dst + 16 * full);
+}
+
+__attribute__((target("avx512bw,avx512vl,bmi2"), noinline)) void tail_avx512(const uint8_t *src,
+                                                                             int rem,
+                                                                             uint8_t *dst) {
+    block_avx512(src, (1ull << rem) - 1ull, dst);
+}
+
+// AVX2 body (measured faster than the 512-bit loop on the B200 hosts: 98 vs 81 GB/s with 16
+// threads) with the masked 512-bit load for the partial block.
+__attribute__((target("avx2,bmi2"))) void contig_avx2_tail512(const uint8_t *src, int64_t len,
+                                                              uint8_t *dst) {
+    const int64_t full = len / 64;
+    for (int64_t i = 0; i < full; ++i) {
+        const uint64_t w0 = half_avx2(src + 64 * i), w1 = half_avx2(src + 64 * i + 32);
+        store16(dst + 16 * i, w0, w1);
+    }
+    if (len > 64 * full) tail_avx512(src + 64 * full, static_cast<int>(len - 64 * full), dst + 16 * full);
+}
+
+void contig_scalar(const uint8_t *src, int64_t len, uint8_t *dst) {
+    const int64_t full = len / 64;
+    for (int64_t i = 0; i < full; ++i) tail_scalar(src + 64 * i, 64, dst + 16 * i);
+    if (len > 64 * full) tail_scalar(src + 64 * full, len - 64 * full, dst + 16 * full);
+}
+
+typedef void (*contig_fn)(const uint8_t *, int64_t, uint8_t *);
+
+// level: -1 best available, 0 scalar, 1 AVX2, 2 AVX-512, 3 AVX2 body + AVX-512 tail; a level
+// the CPU lacks falls back
+contig_fn pick(int level) {
+    __builtin_cpu_init();
+    const bool bmi2 = __builtin_cpu_supports("bmi2");
+    const bool has512 = bmi2 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
+    const bool has2 = bmi2 && __builtin_cpu_supports("avx2");
+    if (level < 0) level = 3;
+    if (level >= 3 && has512 && has2) return contig_avx2_tail512;
+    if (level >= 2 && has512) return contig_avx512;
+    if (level >= 1 && has2) return contig_avx2;
+    return contig_scalar;
+}
+
+}  // namespace
+
+// Pack contigs [c0, c1): contig c has offsets[c+1] - offsets[c] ASCII bases at bases +
+// offsets[c]; its packed words start at packed + 4 * first_word[c * word_stride] bytes
+// (first_word addressed with a byte stride so that it can point into an array of structs).
+// level: -1 best available, 0 scalar, 1 AVX2, 2 AVX-512, 3 AVX2 + 512-bit tail (tests force
+// the variants).
+extern "C" void mcg_hostpack_range(const uint8_t *bases, const int64_t *offsets, int64_t c0,
+                                   int64_t c1, const void *first_word, int64_t word_stride_bytes,
+                                   uint8_t *packed, int level) {
+    static contig_fn best = pick(-1);
+    const contig_fn fn = level < 0 ? best : pick(level);
+    const char *fw = static_cast<const char *>(first_word);
+    for (int64_t c = c0; c < c1; ++c) {
+        int64_t word;
+        memcpy(&word, fw + c * word_stride_bytes, sizeof word);
+        fn(bases + offsets[c], offsets[c + 1] - offsets[c], packed + 4 * word);
+    }
+    _mm_sfence();   // the non-temporal stores are visible before the chunk is reported packed
+}
+
+// the variant `level = -1` resolves to on this CPU
+extern "C" int mcg_hostpack_level(void) {
+    const contig_fn fn = pick(-1);
+    return fn == contig_avx2_tail512 ? 3 : fn == contig_avx512 ? 2 : fn == contig_avx2 ? 1 : 0;
+}

@@ -38,6 +38,13 @@ struct mcg_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // H2D of contig chunks, overlapped with packing
+    cudaStream_t copy_stream2 = nullptr;  // H2D of host-packed chunks
+    cudaEvent_t copy2_done = nullptr;
+    void *pinned_pack = nullptr;          // host-packed contigs, staged for the copy engine
+    size_t pinned_pack_cap = 0;
+    int host_pack_threads = -1;           // -1: MCG_HOST_PACK_THREADS or the hardware threads
+    int64_t ingest_stats[4] = {};         // last ASCII load: h2d bytes, host-packed bases,
+                                          // GPU-packed bases, host threads
     cudaEvent_t copy_ev[4] = {};
     cudaEvent_t copy_start = nullptr;
     std::mutex mu;
