@@ -123,6 +123,17 @@ class GpuBackend:
                                                  cen_cov=cen_cov)
             return arg, w
 
+    def pair_matrix(self, prof, cov):
+        """All-pairs (prob_comp, -log10 weight) of the rows of dense [n,136] / [n,S] tables:
+        one launch for the bin x bin merge scoring (metacoag:1104-1131)."""
+        with self._lock:
+            self._key = None        # the tables replace the resident contig features
+            self.ctx.set_profiles(prof)
+            self.ctx.load_coverage(cov)
+            ids = np.arange(prof.shape[0], dtype=np.int64)
+            out = self.ctx.pair_scores(ids, ids, want=("pc", "lp"))
+            return out["pc"], out["lp"]
+
     def bfs_candidates(self, indptr, indices, labels, starts, depth_limit):
         with self._lock:
             return self.ctx.bfs_candidates(indptr, indices, labels, starts, depth_limit)

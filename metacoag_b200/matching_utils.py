@@ -198,3 +198,54 @@ def further_match_contigs(unbinned_mg_contigs, min_length, bins, n_bins, bin_of_
             bin_markers[b] = list(set(bin_markers[b] + contig_markers[contigid]))
 
     return bins, bin_of_contig, n_bins, bin_markers, binned_contigs_with_markers
+
+
+# ---- bin x bin merge scoring (metacoag:1090-1143, inline in the reference's CLI) --------------
+def bin_merge_candidates(bins, bin_markers, bin_seed_tetramer_profiles,
+                         bin_seed_coverage_profiles, w_intra, n_mg, bin_mg_threshold):
+    """The pair loop of the bin-merge step as one batched call.
+
+    The reference scores, for every bin ``b`` and every bin ``pb`` whose marker genes do not
+    overlap with ``b``'s, the seed centroids against each other (get_tetramer_distance,
+    get_comp_probability, get_cov_probability, metacoag:1108-1121) and links ``b`` to the
+    first ``pb`` with the smallest weight among those with weight <= w_intra (strict ``<``,
+    metacoag:1138-1140); a bin with no candidate and fewer than ``n_mg * bin_mg_threshold``
+    marker genes is marked for removal (metacoag:1146-1147).  Here all B x B weights come
+    from one launch; the marker tests, the order of ``bin_markers`` and the strict-minimum
+    rule stay as they are.
+
+    Returns ``(edges, bins_to_rem)``: ``edges`` is the list of ``(b, min_pb)`` in the order
+    the reference would call ``bins_graph.add_edge``.
+    """
+    order = list(bin_markers)
+    pos = {b: i for i, b in enumerate(order)}
+    missing = [b for b in bins if b not in pos]
+    if missing:
+        raise KeyError(missing[0])
+    prof = np.array([np.asarray(bin_seed_tetramer_profiles[b], dtype=np.float64) for b in order])
+    cov = np.array([np.asarray(bin_seed_coverage_profiles[b], dtype=np.float64) for b in order])
+    prof = prof.reshape(len(order), -1)
+    cov = cov.reshape(len(order), -1)
+    if (cov <= 0).any():
+        raise ValueError("math domain error")      # math.log(0), matching_utils.py:49
+    pc, lp = _backend.backend().pair_matrix(prof, cov)
+    marker_sets = {b: set(bin_markers[b]) for b in order}
+    edges, bins_to_rem = [], []
+    for b in bins:
+        min_pb, min_pb_weight = -1, MAX_WEIGHT
+        for pb in order:
+            if marker_sets[pb] & marker_sets[b]:
+                continue
+            i, j = pos[b], pos[pb]
+            if math.isnan(pc[i, j]):
+                raise ZeroDivisionError("float division by zero")   # matching_utils.py:36-39
+            log_prob = float(lp[i, j])
+            # (the reference recomputes the same weight once more before accepting it)
+            if log_prob <= w_intra and log_prob < min_pb_weight:
+                min_pb_weight = log_prob
+                min_pb = pb
+        if min_pb != -1:
+            edges.append((b, min_pb))
+        elif len(bin_markers[b]) < n_mg * bin_mg_threshold:
+            bins_to_rem.append(b)
+    return edges, bins_to_rem

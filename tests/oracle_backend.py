@@ -56,6 +56,16 @@ class OracleBackend:
         arg, w, _ = oracle.score_centroids(prof, cov, cen_prof, cen_cov, queries=queries)
         return arg, w
 
+    def pair_matrix(self, prof, cov):
+        n = prof.shape[0]
+        pc = np.zeros((n, n))
+        lp = np.zeros((n, n))
+        for i in range(n):
+            for j in range(n):
+                pc[i, j] = oracle.comp_prob(oracle.euclidean(prof[i], prof[j]))
+                lp[i, j] = oracle.pair_lp(prof[i], prof[j], cov[i], cov[j])[1]
+        return pc, lp
+
     def bfs_candidates(self, indptr, indices, labels, starts, depth_limit):
         hits = [ref_bfs(int(s), depth_limit, labels, indptr, indices) for s in starts]
         width = max([len(h) for h in hits] + [1])
