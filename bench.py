@@ -410,6 +410,18 @@ def main():
                      gbases_per_s=n_bases / (kernel_ms["scan"] * 1e-3) / 1e9,
                      note="issue / shared-memory bound by design (DESIGN.md 4.1): ~11 "
                           "instructions per base against 2 for 70 % of HBM")
+    # The scan is not HBM-bound: its counters live in shared memory and every window costs a
+    # byte load and a byte store there.  The crossbar moves one 128-byte wavefront per clock per
+    # SM; the wavefront count per launch comes from the same ncu capture as `traffic`.
+    wf = captured.get(wl_key, {}).get("scan_kernel_smem_wavefronts")
+    if wf:
+        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        peak_wf = 148 * sm_clock
+        scan_roof["binding"] = {"resource": "shared-memory crossbar (wavefronts/s)",
+                                "achieved": wf / (kernel_ms["scan"] * 1e-3), "peak": peak_wf,
+                                "frac": wf / (kernel_ms["scan"] * 1e-3) / peak_wf,
+                                "wavefronts_per_launch": wf,
+                                "floor_wavefronts": 2.0 * n_bases / 32.0}
     kernels = [scan_roof]
     if kernel_ms.get("distance", 0.0) > 0.0:
         # SURVEY 8d splits F_pair = 431 + 14 S into 136*3 for the distance and the rest

@@ -99,6 +99,17 @@ int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads);
  * masked 512-bit tail; a level the CPU lacks falls back to the next lower one. */
 int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, int64_t n, uint8_t *packed,
                        int level);
+/* feature_utils.py:131-138, 182-186: the contigs are read with Bio.SeqIO.parse(path,
+ * "fasta"), keeping record.id and str(record.seq).  These two host-only calls produce the same
+ * names and sequences (BioPython's SimpleFastaParser rules: text before the first '>' skipped,
+ * id = first word of the header, lines right-stripped, ' ' removed, "\n" / "\r\n" / "\r" line
+ * ends) as one byte blob + offsets, ready for mcg_load_contigs, instead of a list of Python
+ * strings.  mcg_fasta_index sizes the outputs; mcg_fasta_load fills caller-owned buffers
+ * (bases[n_bases], offsets[n_records + 1], names[name_bytes], name_offsets[n_records + 1]).
+ * Return 0, -1 if the file cannot be read, -2 if it changed between the two calls. */
+int mcg_fasta_index(const char *path, int64_t *n_records, int64_t *n_bases, int64_t *name_bytes);
+int mcg_fasta_load(const char *path, uint8_t *bases, int64_t *offsets, uint8_t *names,
+                   int64_t *name_offsets, int64_t n_records, int64_t n_bases, int64_t name_bytes);
 /* Last ASCII load: stats[0] bytes copied host->device for the bases, [1] bases packed by
  * host threads, [2] bases packed by the kernel, [3] host threads used. */
 int mcg_ingest_stats(mcg_ctx *ctx, int64_t stats[4]);

@@ -69,6 +69,8 @@ SIGNATURES = {
     "mcg_set_host_pack_threads": (_int, [_vp, _int]),
     "mcg_ingest_stats": (_int, [_vp, _vp]),
     "mcg_pack_2bit_host": (_int, [_vp, _vp, _i64, _vp, _int]),
+    "mcg_fasta_index": (_int, [_c.c_char_p, _vp, _vp, _vp]),
+    "mcg_fasta_load": (_int, [_c.c_char_p, _vp, _vp, _vp, _vp, _i64, _i64, _i64]),
 }
 
 
@@ -122,6 +124,35 @@ def pack_2bit_host(bases, offsets, level=-1):
     if rc != OK:
         raise McgError(rc, "mcg_pack_2bit_host failed")
     return out
+
+
+def device_count():
+    return int(load_library().mcg_device_count())
+
+
+def read_fasta(path, pinned=False):
+    """FASTA file -> (names list[str], bases uint8[n_bases], offsets int64[n+1]) with the
+    library's host reader (BioPython FASTA semantics, include/mcg_b200.h).  ``pinned`` puts
+    the bases into page-locked memory (needs a CUDA device) so that mcg_load_contigs can hand
+    them to the copy engine directly."""
+    lib = load_library()
+    raw = os.fsencode(path)
+    n, nb, nn = _c.c_int64(0), _c.c_int64(0), _c.c_int64(0)
+    rc = lib.mcg_fasta_index(raw, _c.byref(n), _c.byref(nb), _c.byref(nn))
+    if rc != 0:
+        raise FileNotFoundError(path)
+    n, nb, nn = n.value, nb.value, nn.value
+    bases = pinned_empty(nb) if (pinned and nb) else np.empty(nb, dtype=np.uint8)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    names = np.empty(nn, dtype=np.uint8)
+    name_offsets = np.zeros(n + 1, dtype=np.int64)
+    rc = lib.mcg_fasta_load(raw, _ptr(bases), _ptr(offsets), _ptr(names), _ptr(name_offsets),
+                            n, nb, nn)
+    if rc != 0:
+        raise OSError("mcg_fasta_load(%s) failed (%d)" % (path, rc))
+    text = names.tobytes().decode("latin-1")
+    no = name_offsets.tolist()
+    return [text[no[i]:no[i + 1]] for i in range(n)], bases, offsets
 
 
 class Context:

@@ -150,3 +150,152 @@ extern "C" int mcg_hostpack_level(void) {
     const contig_fn fn = pick(-1);
     return fn == contig_avx2_tail512 ? 3 : fn == contig_avx512 ? 2 : fn == contig_avx2 ? 1 : 0;
 }
+
+// ---- FASTA -> contig blob ---------------------------------------------------------------------
+//   reference: feature_utils.py:131-138, 182-186 read the contigs with Bio.SeqIO.parse(path,
+//   "fasta") and keep str(record.seq) and record.id.  BioPython's FASTA reader (Bio.SeqIO.FastaIO
+//   SimpleFastaParser) does, on a text-mode handle with universal newlines:
+//     - skip everything before the first line that starts with '>';
+//     - title = line[1:].rstrip(); id = first whitespace-separated word of the title ("" if none);
+//     - sequence = "".join(line.rstrip() for the following lines) with every ' ' and '\r' removed.
+//   The two passes below produce exactly that, as one byte blob + offsets instead of a list of
+//   Python strings: pass 1 sizes the outputs, pass 2 fills caller-owned
+//   (pinned) buffers.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+
+inline bool py_space(uint8_t c) {   // str.isspace() on the ASCII range
+    return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31);
+}
+
+struct FastaOut {
+    uint8_t *bases = nullptr;
+    int64_t *offsets = nullptr;
+    uint8_t *names = nullptr;
+    int64_t *name_offsets = nullptr;
+    int64_t n_records = 0, n_bases = 0, name_bytes = 0;
+};
+
+// One logical line [p, e) (terminator excluded).
+template <bool FILL>
+inline void fasta_line(const uint8_t *p, const uint8_t *e, bool *in_record, FastaOut *o) {
+    if (p < e && *p == '>') {
+        *in_record = true;
+        const uint8_t *q = p + 1;
+        while (e > q && py_space(e[-1])) --e;        // rstrip
+        while (q < e && py_space(*q)) ++q;           // split(None, 1)[0]
+        const uint8_t *w = q;
+        while (w < e && !py_space(*w)) ++w;
+        if (FILL) {
+            o->name_offsets[o->n_records] = o->name_bytes;
+            memcpy(o->names + o->name_bytes, q, static_cast<size_t>(w - q));
+            o->offsets[o->n_records] = o->n_bases;
+        }
+        o->name_bytes += w - q;
+        o->n_records += 1;
+        return;
+    }
+    if (!*in_record) return;
+    while (e > p && py_space(e[-1])) --e;            // rstrip
+    if (e <= p) return;
+    if (memchr(p, ' ', static_cast<size_t>(e - p)) == nullptr) {
+        if (FILL) memcpy(o->bases + o->n_bases, p, static_cast<size_t>(e - p));
+        o->n_bases += e - p;
+    } else {
+        for (; p < e; ++p)
+            if (*p != ' ') {   // ('\r' never reaches here: it ends a line)
+                if (FILL) o->bases[o->n_bases] = *p;
+                o->n_bases += 1;
+            }
+    }
+}
+
+template <bool FILL> void fasta_pass(const uint8_t *data, size_t size, FastaOut *o) {
+    bool in_record = false;
+    const uint8_t *p = data, *end = data + size;
+    while (p < end) {
+        // universal newlines: '\n', "\r\n" and a lone '\r' all end a line
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(p, '\n', static_cast<size_t>(end - p)));
+        const uint8_t *e = nl ? nl : end;
+        const uint8_t *next = nl ? nl + 1 : end;
+        const uint8_t *cr = static_cast<const uint8_t *>(memchr(p, '\r', static_cast<size_t>(e - p)));
+        if (cr) {
+            e = cr;
+            next = cr + 1;
+            if (next < end && *next == '\n') ++next;
+        }
+        fasta_line<FILL>(p, e, &in_record, o);
+        p = next;
+    }
+    if (FILL && o->n_records) {
+        o->offsets[o->n_records] = o->n_bases;
+        o->name_offsets[o->n_records] = o->name_bytes;
+    }
+}
+
+struct Mapped {
+    const uint8_t *data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    bool open(const char *path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return false;
+        size = static_cast<size_t>(st.st_size);
+        if (size == 0) return true;
+        void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        madvise(m, size, MADV_SEQUENTIAL);
+        data = static_cast<const uint8_t *>(m);
+        return true;
+    }
+    ~Mapped() {
+        if (data) munmap(const_cast<uint8_t *>(data), size);
+        if (fd >= 0) close(fd);
+    }
+};
+
+}  // namespace
+
+// Pass 1.  Returns 0, or -1 when the file cannot be read.
+extern "C" int mcg_fasta_index(const char *path, int64_t *n_records, int64_t *n_bases,
+                                   int64_t *name_bytes) {
+    Mapped m;
+    if (!m.open(path)) return -1;
+    FastaOut o;
+    fasta_pass<false>(m.data, m.size, &o);
+    *n_records = o.n_records;
+    *n_bases = o.n_bases;
+    *name_bytes = o.name_bytes;
+    return 0;
+}
+
+// Pass 2 into buffers sized by pass 1 (offsets and name_offsets have n_records + 1 entries).
+// Returns 0, -1 when the file cannot be read, -2 when it changed between the passes.
+extern "C" int mcg_fasta_load(const char *path, uint8_t *bases, int64_t *offsets, uint8_t *names,
+                                  int64_t *name_offsets, int64_t n_records, int64_t n_bases,
+                                  int64_t name_bytes) {
+    Mapped m;
+    if (!m.open(path)) return -1;
+    FastaOut sized;
+    fasta_pass<false>(m.data, m.size, &sized);
+    if (sized.n_records != n_records || sized.n_bases != n_bases || sized.name_bytes != name_bytes)
+        return -2;
+    FastaOut o;
+    o.bases = bases;
+    o.offsets = offsets;
+    o.names = names;
+    o.name_offsets = name_offsets;
+    if (n_records == 0) {
+        offsets[0] = 0;
+        name_offsets[0] = 0;
+        return 0;
+    }
+    fasta_pass<true>(m.data, m.size, &o);
+    return 0;
+}

@@ -55,9 +55,55 @@ def compute_kmer_inds(k):
     return slots, n_slots
 
 
+class ContigBlob:
+    """The contig sequences as one byte blob + offsets that still reads like the reference's
+    ``sequences`` list (``len``, indexing, slicing and iteration give ``str``): what
+    get_cov_len / get_cov_len_megahit return here.  get_tetramer_profiles hands ``blob`` and
+    ``offsets`` to the C ABI as they are instead of joining 10^5..10^6 Python strings
+    (SURVEY.md 8f item 1)."""
+
+    def __init__(self, blob, offsets):
+        self.blob = blob
+        self.offsets = np.asarray(offsets, dtype=np.int64)
+
+    def __len__(self):
+        return self.offsets.shape[0] - 1
+
+    def _one(self, i):
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("list index out of range")
+        return self.blob[self.offsets[i]:self.offsets[i + 1]].tobytes().decode("latin-1")
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(j) for j in range(*i.indices(len(self)))]
+        return self._one(int(i))
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self._one(i)
+
+    def needs_strip(self):
+        """count_kmers strips the sequence (:63); true when that would change any record
+        (lines are right-stripped by the reader, so only a leading tab-like byte can)."""
+        n = len(self)
+        if n == 0 or self.blob.shape[0] == 0:
+            return False
+        lens = np.diff(self.offsets)
+        first = self.blob[np.minimum(self.offsets[:-1], self.blob.shape[0] - 1)][lens > 0]
+        last = self.blob[np.maximum(self.offsets[1:] - 1, 0)][lens > 0]
+        edge = np.concatenate([first, last])
+        return bool((((edge >= 9) & (edge <= 13)) | (edge == 32) | ((edge >= 28) & (edge <= 31))).any())
+
+
 def _ascii_blob(sequences):
     """One contiguous uint8 blob + offsets from the reference's list of strings, with the
     ``str.strip()`` count_kmers applies (:63)."""
+    if isinstance(sequences, ContigBlob) and not sequences.needs_strip():
+        return sequences.blob, sequences.offsets
     parts = []
     for seq in sequences:
         seq = str(seq)
@@ -108,20 +154,30 @@ def get_tetramer_profiles(output_path, sequences, contigs_file, contig_lengths, 
 
 
 def _fasta_records(path):
-    """(name, sequence) per record; name = first word of the header, what Bio.SeqIO calls
-    ``record.id`` (the reference reads FASTA with BioPython, :131, :182)."""
+    """(name, sequence) per record, pure Python: BioPython's SimpleFastaParser restated (the
+    reference reads FASTA with Bio.SeqIO, :131, :182) -- text before the first '>' skipped,
+    name = first word of the header (``record.id``), lines right-stripped and joined, spaces
+    removed.  The library's reader (mcg_fasta_load) is checked against this one."""
     name, chunks = None, []
-    with open(path) as handle:
+    with open(path, encoding="latin-1") as handle:
         for line in handle:
-            if line.startswith(">"):
+            if line[:1] == ">":
                 if name is not None:
-                    yield name, "".join(chunks)
-                words = line[1:].split()
+                    yield name, "".join(chunks).replace(" ", "").replace("\r", "")
+                words = line[1:].rstrip().split(None, 1)
                 name, chunks = (words[0] if words else ""), []
             elif name is not None:
-                chunks.append(line.strip())
+                chunks.append(line.rstrip())
     if name is not None:
-        yield name, "".join(chunks)
+        yield name, "".join(chunks).replace(" ", "").replace("\r", "")
+
+
+def _read_contigs(contigs_file):
+    """(names, sequences) of a FASTA file through the library's host reader: the sequences
+    come back as a ContigBlob (pinned when a CUDA device is there, so that the upload needs
+    no staging copy)."""
+    names, blob, offsets = _lib.read_fasta(contigs_file, pinned=_lib.device_count() > 0)
+    return names, ContigBlob(blob, offsets)
 
 
 def _read_abundance(abundance_file, contig_num_of, contig_lengths, min_length, coverages):
@@ -154,10 +210,9 @@ def get_cov_len(contigs_file, contig_names_rev, min_length, abundance_file):
     reference's; an unknown contig name raises KeyError."""
     coverages = defaultdict(lambda: [0])
     contig_lengths = defaultdict(int)
-    sequences = []
-    for name, seq in _fasta_records(contigs_file):
-        contig_lengths[contig_names_rev[name]] = len(seq)
-        sequences.append(seq)
+    names, sequences = _read_contigs(contigs_file)
+    for name, length in zip(names, np.diff(sequences.offsets).tolist()):
+        contig_lengths[contig_names_rev[name]] = length
     n_samples = _read_abundance(abundance_file, lambda name: contig_names_rev[name],
                                 contig_lengths, min_length, coverages)
     return sequences, coverages, contig_lengths, n_samples
@@ -166,10 +221,10 @@ def get_cov_len(contigs_file, contig_names_rev, min_length, abundance_file):
 def get_cov_len_megahit(contigs_file, contig_names_rev, graph_to_contig_map_rev, min_length,
                         abundance_file):
     """MEGAHIT flavour: FASTA names map to graph names first (:168-214)."""
-    coverages, contig_lengths, sequences = {}, {}, []
-    for name, seq in _fasta_records(contigs_file):
-        contig_lengths[contig_names_rev[graph_to_contig_map_rev[name]]] = len(seq)
-        sequences.append(seq)
+    coverages, contig_lengths = {}, {}
+    names, sequences = _read_contigs(contigs_file)
+    for name, length in zip(names, np.diff(sequences.offsets).tolist()):
+        contig_lengths[contig_names_rev[graph_to_contig_map_rev[name]]] = length
     n_samples = _read_abundance(
         abundance_file, lambda name: contig_names_rev[graph_to_contig_map_rev[name]],
         contig_lengths, min_length, coverages)

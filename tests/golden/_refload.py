@@ -23,20 +23,32 @@ class _Record:
 
 
 def _parse_fasta(path, fmt):
+    """Bio.SeqIO.parse(path, "fasta") as far as the reference uses it.  The rules are those of
+    Bio.SeqIO.FastaIO.SimpleFastaParser (BioPython 1.7x/1.8x): text before the first '>' line is
+    skipped; title = line[1:].rstrip(); id = first word of the title; the sequence is the
+    right-stripped lines joined, with ' ' and '\\r' removed; the handle is text mode."""
     assert fmt == "fasta"
-    name, desc, chunks = None, None, []
     with open(path) as fh:
+        title = None
         for line in fh:
-            if line.startswith(">"):
-                if name is not None:
-                    yield _Record(name, desc, "".join(chunks))
-                desc = line[1:].rstrip("\n")
-                name = desc.split()[0] if desc.split() else ""
-                chunks = []
-            else:
-                chunks.append(line.strip())
-    if name is not None:
-        yield _Record(name, desc, "".join(chunks))
+            if line[0] == ">":
+                title = line[1:].rstrip()
+                break
+        if title is None:
+            return
+        lines = []
+        for line in fh:
+            if line[0] == ">":
+                words = title.split(None, 1)
+                yield _Record(words[0] if words else "", title,
+                              "".join(lines).replace(" ", "").replace("\r", ""))
+                lines = []
+                title = line[1:].rstrip()
+                continue
+            lines.append(line.rstrip())
+        words = title.split(None, 1)
+        yield _Record(words[0] if words else "", title,
+                      "".join(lines).replace(" ", "").replace("\r", ""))
 
 
 class ShimGraph:
