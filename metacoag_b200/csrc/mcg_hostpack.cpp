@@ -178,6 +178,8 @@ struct FastaOut {
     uint8_t *names = nullptr;
     int64_t *name_offsets = nullptr;
     int64_t n_records = 0, n_bases = 0, name_bytes = 0;
+    int64_t cap_records = 0, cap_bases = 0, cap_names = 0;   // pass 2: sizes of the buffers
+    bool overflow = false;
 };
 
 // One logical line [p, e) (terminator excluded).
@@ -191,6 +193,10 @@ inline void fasta_line(const uint8_t *p, const uint8_t *e, bool *in_record, Fast
         const uint8_t *w = q;
         while (w < e && !py_space(*w)) ++w;
         if (FILL) {
+            if (o->n_records >= o->cap_records || o->name_bytes + (w - q) > o->cap_names) {
+                o->overflow = true;
+                return;
+            }
             o->name_offsets[o->n_records] = o->name_bytes;
             memcpy(o->names + o->name_bytes, q, static_cast<size_t>(w - q));
             o->offsets[o->n_records] = o->n_bases;
@@ -202,13 +208,20 @@ inline void fasta_line(const uint8_t *p, const uint8_t *e, bool *in_record, Fast
     if (!*in_record) return;
     while (e > p && py_space(e[-1])) --e;            // rstrip
     if (e <= p) return;
+    if (FILL && o->overflow) return;
     if (memchr(p, ' ', static_cast<size_t>(e - p)) == nullptr) {
-        if (FILL) memcpy(o->bases + o->n_bases, p, static_cast<size_t>(e - p));
+        if (FILL) {
+            if (o->n_bases + (e - p) > o->cap_bases) { o->overflow = true; return; }
+            memcpy(o->bases + o->n_bases, p, static_cast<size_t>(e - p));
+        }
         o->n_bases += e - p;
     } else {
         for (; p < e; ++p)
             if (*p != ' ') {   // ('\r' never reaches here: it ends a line)
-                if (FILL) o->bases[o->n_bases] = *p;
+                if (FILL) {
+                    if (o->n_bases >= o->cap_bases) { o->overflow = true; return; }
+                    o->bases[o->n_bases] = *p;
+                }
                 o->n_bases += 1;
             }
     }
@@ -231,7 +244,7 @@ template <bool FILL> void fasta_pass(const uint8_t *data, size_t size, FastaOut 
         fasta_line<FILL>(p, e, &in_record, o);
         p = next;
     }
-    if (FILL && o->n_records) {
+    if (FILL && o->n_records && !o->overflow) {
         o->offsets[o->n_records] = o->n_bases;
         o->name_offsets[o->n_records] = o->name_bytes;
     }
@@ -282,11 +295,10 @@ extern "C" int mcg_fasta_load(const char *path, uint8_t *bases, int64_t *offsets
                                   int64_t name_bytes) {
     Mapped m;
     if (!m.open(path)) return -1;
-    FastaOut sized;
-    fasta_pass<false>(m.data, m.size, &sized);
-    if (sized.n_records != n_records || sized.n_bases != n_bases || sized.name_bytes != name_bytes)
-        return -2;
     FastaOut o;
+    o.cap_records = n_records;
+    o.cap_bases = n_bases;
+    o.cap_names = name_bytes;
     o.bases = bases;
     o.offsets = offsets;
     o.names = names;
@@ -297,5 +309,7 @@ extern "C" int mcg_fasta_load(const char *path, uint8_t *bases, int64_t *offsets
         return 0;
     }
     fasta_pass<true>(m.data, m.size, &o);
+    if (o.overflow || o.n_records != n_records || o.n_bases != n_bases || o.name_bytes != name_bytes)
+        return -2;
     return 0;
 }
