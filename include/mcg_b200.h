@@ -179,6 +179,16 @@ int mcg_bfs_candidates(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indic
                        int32_t *hit_node, int32_t *hit_bin, int32_t *hit_depth,
                        int32_t *n_hits);
 
+/* matching_utils.py:191-197 and :285-292 (graph gate of match_contigs): for every
+ * (source, target) pair, len(assembly_graph.get_shortest_paths(source, to=target)[0]) -- the
+ * number of vertices on a shortest path over the CSR assembly graph, 1 when source ==
+ * target, 0 when the target cannot be reached.  out is [n_sources, n_targets].  All sources
+ * advance together (bit-parallel multi-source BFS, 32 per pass) instead of one igraph BFS
+ * per pair. */
+int mcg_path_lengths(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
+                     int64_t n_vertices, const int64_t *sources, int64_t n_sources,
+                     const int64_t *targets, int64_t n_targets, int32_t *out);
+
 /* ---- fused plug-in call and the resident step ---------------------------------- */
 /* Featurise + score in one call from HOST buffers: upload, pack, scan, normalise,
  * coverage terms, rule-C scoring against the given centroids, download

@@ -56,6 +56,43 @@ def csr_bins(bins, bin_order, counts=None):
     return np.asarray(members, dtype=np.int64), np.asarray(seg, dtype=np.int64)
 
 
+class GraphCache:
+    """CSR copy of the duck-typed assembly graph (``neighbors(v, mode="ALL")``), built once
+    per graph object; neighbour order is kept as the graph reports it."""
+
+    def __init__(self):
+        self.key = None
+        self.indptr = self.indices = None
+
+    def get(self, assembly_graph, n_vertices):
+        key = (id(assembly_graph), n_vertices)
+        if key != self.key:
+            indptr = np.zeros(n_vertices + 1, dtype=np.int64)
+            chunks = []
+            for v in range(n_vertices):
+                nb = assembly_graph.neighbors(v, mode="ALL")
+                indptr[v + 1] = indptr[v] + len(nb)
+                chunks.append(np.asarray(nb, dtype=np.int32))
+            self.indices = (np.concatenate(chunks) if chunks and indptr[-1] > 0
+                            else np.zeros(0, dtype=np.int32))
+            self.indptr = indptr
+            self.key = key
+        return self.indptr, self.indices
+
+
+graphs = GraphCache()
+
+
+def vertex_count(assembly_graph, *dicts):
+    if hasattr(assembly_graph, "vcount"):
+        return int(assembly_graph.vcount())
+    n = 0
+    for d in dicts:
+        if len(d):
+            n = max(n, max(d) + 1)
+    return n
+
+
 class GpuBackend:
     """Scoring through the C ABI; one resident contig table per (profiles, coverages) pair."""
 
@@ -137,6 +174,11 @@ class GpuBackend:
     def bfs_candidates(self, indptr, indices, labels, starts, depth_limit):
         with self._lock:
             return self.ctx.bfs_candidates(indptr, indices, labels, starts, depth_limit)
+
+    def path_lengths(self, indptr, indices, sources, targets):
+        """[len(sources), len(targets)] vertices on a shortest path, 0 = unreachable."""
+        with self._lock:
+            return self.ctx.path_lengths(indptr, indices, sources, targets)
 
     # -- scalar primitives --------------------------------------------------------------------
     def normpdf(self, x, mean, sd):

@@ -55,6 +55,7 @@ SIGNATURES = {
     "mcg_score_members": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _vp]),
     "mcg_bfs_candidates": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _vp, _vp,
                                   _vp, _vp]),
+    "mcg_path_lengths": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "mcg_featurise_score": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _i64, _vp,
                                    _vp]),
     "mcg_set_centroids": (_int, [_vp, _vp, _vp, _i64]),
@@ -393,6 +394,18 @@ class Context:
             if ns == 0 or int(n_hits.max()) <= max_hits:
                 return node, bin_, depth, n_hits
             max_hits = int(n_hits.max())
+
+    def path_lengths(self, indptr, indices, sources, targets):
+        """[len(sources), len(targets)] int32: vertices on a shortest path, 0 = unreachable."""
+        indptr = _arr(indptr, np.int64)
+        indices = _arr(indices, np.int32)
+        sources = _arr(sources, np.int64)
+        targets = _arr(targets, np.int64)
+        out = np.zeros((sources.shape[0], targets.shape[0]), dtype=np.int32)
+        self._check(self.lib.mcg_path_lengths(
+            self.handle, _ptr(indptr), _ptr(indices), indptr.shape[0] - 1, _ptr(sources),
+            sources.shape[0], _ptr(targets), targets.shape[0], _ptr(out)))
+        return out
 
     # -- fused / resident ---------------------------------------------------------------------
     def featurise_score(self, bases, offsets, cov, cen_prof, cen_cov, encoding=ENC_ASCII,

@@ -1003,6 +1003,62 @@ extern "C" int mcg_bfs_candidates(mcg_ctx *ctx, const int64_t *indptr, const int
     return MCG_OK;
 }
 
+extern "C" int mcg_path_lengths(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
+                                int64_t n_vertices, const int64_t *sources, int64_t n_sources,
+                                const int64_t *targets, int64_t n_targets, int32_t *out) {
+    MCG_ENTER(ctx);
+    if (n_vertices <= 0 || n_sources < 0 || n_targets < 0 || !indptr || !out)
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    if (n_sources == 0 || n_targets == 0) return MCG_OK;
+    if (n_vertices > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many vertices");
+    MCG_TRY(check_ids(ctx, sources, n_sources, n_vertices, "sources"));
+    MCG_TRY(check_ids(ctx, targets, n_targets, n_vertices, "targets"));
+    const int64_t n_edges = indptr[n_vertices];
+    if (n_edges > 0 && !indices) return mcg_fail(ctx, MCG_ERR_ARG, "indices is NULL");
+    // column of every distinct target vertex; duplicates in `targets` share a column
+    std::vector<int32_t> tslot(static_cast<size_t>(n_vertices), -1);
+    std::vector<int64_t> col_of(static_cast<size_t>(n_targets));
+    int64_t n_cols = 0;
+    for (int64_t j = 0; j < n_targets; ++j) {
+        int32_t &slot = tslot[static_cast<size_t>(targets[j])];
+        if (slot < 0) slot = static_cast<int32_t>(n_cols++);
+        col_of[j] = slot;
+    }
+    DevBuf d_indptr, d_indices, d_tslot, d_sources, d_work, d_counts, d_out;
+    int rc = MCG_OK;
+    auto cleanup = [&]() {
+        for (DevBuf *b : {&d_indptr, &d_indices, &d_tslot, &d_sources, &d_work, &d_counts, &d_out})
+            if (b->p) cudaFree(b->p);
+    };
+#define PL_TRY(expr) do { rc = (expr); if (rc != MCG_OK) { cleanup(); return rc; } } while (0)
+    PL_TRY(mcg_reserve(ctx, d_indptr, sizeof(int64_t) * (n_vertices + 1)));
+    PL_TRY(mcg_reserve(ctx, d_indices, sizeof(int32_t) * std::max<int64_t>(n_edges, 1)));
+    PL_TRY(mcg_reserve(ctx, d_tslot, sizeof(int32_t) * n_vertices));
+    PL_TRY(mcg_reserve(ctx, d_sources, sizeof(int64_t) * n_sources));
+    PL_TRY(mcg_reserve(ctx, d_work, sizeof(int32_t) * 6 * n_vertices));
+    PL_TRY(mcg_reserve(ctx, d_counts, 2 * sizeof(int)));
+    PL_TRY(mcg_reserve(ctx, d_out, sizeof(int32_t) * n_sources * n_cols));
+    PL_TRY(h2d(ctx, d_indptr.p, indptr, sizeof(int64_t) * (n_vertices + 1)));
+    if (n_edges) PL_TRY(h2d(ctx, d_indices.p, indices, sizeof(int32_t) * n_edges));
+    PL_TRY(h2d(ctx, d_tslot.p, tslot.data(), sizeof(int32_t) * n_vertices));
+    PL_TRY(h2d(ctx, d_sources.p, sources, sizeof(int64_t) * n_sources));
+    {
+        TimerScope t(ctx, T_OTHER);
+        PL_TRY(mcg_k_path_lengths(ctx, d_indptr.as<int64_t>(), d_indices.as<int32_t>(), n_vertices,
+                                  d_tslot.as<int32_t>(), d_sources.as<int64_t>(), n_sources, n_cols,
+                                  d_work.as<int32_t>(), d_counts.as<int>(), d_out.as<int32_t>()));
+    }
+    std::vector<int32_t> dense(static_cast<size_t>(n_sources * n_cols));
+    PL_TRY(d2h(ctx, dense.data(), d_out.p, sizeof(int32_t) * n_sources * n_cols));
+    PL_TRY(sync(ctx));
+    for (int64_t i = 0; i < n_sources; ++i)
+        for (int64_t j = 0; j < n_targets; ++j)
+            out[i * n_targets + j] = dense[static_cast<size_t>(i * n_cols + col_of[j])];
+    cleanup();
+#undef PL_TRY
+    return MCG_OK;
+}
+
 // ---- fused plug-in call and the resident step ---------------------------------------------------------------------------
 static int step_locked(mcg_ctx *ctx, int32_t *d_argmin, double *d_wmin) {
     if (ctx->n_contigs == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no contigs resident");

@@ -114,3 +114,140 @@ int mcg_k_bfs(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices, i
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }
+
+// ---- shortest-path lengths for the graph gate of match_contigs ----------------------------------
+//
+//   reference: matching_utils.py:191-197 and :285-292 call, for a matched contig v and every
+//   member w of the bin, assembly_graph.get_shortest_paths(v, to=w) and add len(path): the
+//   number of VERTICES on a shortest path (1 when v == w), 0 when w cannot be reached.  igraph
+//   runs one BFS per (v, w) pair.
+//
+// Here up to 32 sources advance together, one bit each (bit-parallel multi-source BFS): a
+// vertex carries the mask of sources that have reached it, a level expands only the vertices
+// whose mask grew (compact frontier lists, so a level costs its frontier, not the graph), and
+// the first time bit s arrives at a target vertex the pair (s, target) gets level + 1 vertices.
+// One cooperative launch walks all levels with two grid-wide barriers per level.
+#include <cooperative_groups.h>
+
+namespace {
+namespace cg = cooperative_groups;
+
+struct PathArgs {
+    const int64_t *indptr;
+    const int32_t *indices;
+    uint32_t *visited, *front_a, *front_b, *next;   // [n] source masks, zero on entry
+    int32_t *list_a, *list_b;                       // [n] frontier vertex lists
+    int *counts;                                    // [2] list lengths, zero on entry
+    const int32_t *tslot;                           // [n] column of the vertex in `out`, or -1
+    const int64_t *sources;                         // [ns] (ns <= 32)
+    int ns;
+    long long nt;
+    int32_t *out;                                   // [ns, nt], zero on entry
+};
+
+__global__ void __launch_bounds__(256) path_lengths_kernel(PathArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+
+    if (tid < a.ns) {
+        const int s = static_cast<int>(a.sources[tid]);
+        const uint32_t bit = 1u << tid;
+        const uint32_t old = atomicOr(&a.visited[s], bit);
+        atomicOr(&a.front_a[s], bit);
+        if (old == 0) a.list_a[atomicAdd(&a.counts[0], 1)] = s;   // the same vertex may be listed as two sources
+        const int col = a.tslot[s];
+        if (col >= 0) a.out[tid * a.nt + col] = 1;
+    }
+    grid.sync();
+
+    uint32_t *front_cur = a.front_a, *front_new = a.front_b;
+    int32_t *list_cur = a.list_a, *list_new = a.list_b;
+    int cur = 0;
+    for (int level = 1;; ++level) {
+        const int n_cur = a.counts[cur];
+        if (n_cur == 0) break;
+        // expand: offer this level's new bits to the neighbours that do not have them yet
+        for (long long i = tid; i < n_cur; i += stride) {
+            const int v = list_cur[i];
+            const uint32_t f = front_cur[v];
+            for (int64_t e = a.indptr[v]; e < a.indptr[v + 1]; ++e) {
+                const int u = a.indices[e];
+                const uint32_t nw = f & ~a.visited[u];
+                if (nw) {
+                    const uint32_t old = atomicOr(&a.next[u], nw);
+                    if (old == 0) list_new[atomicAdd(&a.counts[cur ^ 1], 1)] = u;
+                }
+            }
+        }
+        grid.sync();
+        // every thread has read counts[cur] (n_cur) before that barrier: it can be cleared now
+        // and serves as the output counter of the next level's expansion
+        if (tid == 0) a.counts[cur] = 0;
+        // commit: the offered bits are all new (visited did not change during the expansion)
+        const int n_new = a.counts[cur ^ 1];
+        for (long long i = tid; i < n_new; i += stride) {
+            const int u = list_new[i];
+            const uint32_t nx = a.next[u];
+            a.next[u] = 0;
+            a.visited[u] |= nx;
+            front_new[u] = nx;
+            const int col = a.tslot[u];
+            if (col >= 0)
+                for (uint32_t m = nx; m; m &= m - 1)
+                    a.out[static_cast<long long>(__ffs(m) - 1) * a.nt + col] = level + 1;
+        }
+        for (long long i = tid; i < n_cur; i += stride) front_cur[list_cur[i]] = 0;
+        grid.sync();
+        cur ^= 1;
+        uint32_t *tf = front_cur; front_cur = front_new; front_new = tf;
+        int32_t *tl = list_cur; list_cur = list_new; list_new = tl;
+    }
+}
+
+}  // namespace
+
+// d_work: 7 * n_vertices int32 (zeroed here); d_out [ns, nt] int32.  ns may exceed 32: the
+// sources go in groups of 32.
+int mcg_k_path_lengths(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
+                       int64_t n_vertices, const int32_t *d_tslot, const int64_t *d_sources,
+                       int64_t ns, int64_t nt, int32_t *d_work, int *d_counts, int32_t *d_out) {
+    if (ns == 0 || nt == 0) return MCG_OK;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int supported = 0;
+        MCG_CUDA(ctx, cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, ctx->device));
+        if (!supported) return mcg_fail(ctx, MCG_ERR_CUDA, "cooperative launch not supported");
+        MCG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm,
+                                                                    path_lengths_kernel, 256, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        if (blocks_per_sm > 4) blocks_per_sm = 4;
+    }
+    MCG_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int32_t) * ns * nt, ctx->stream));
+    const size_t n = static_cast<size_t>(n_vertices);
+    for (int64_t s0 = 0; s0 < ns; s0 += 32) {
+        MCG_CUDA(ctx, cudaMemsetAsync(d_work, 0, sizeof(int32_t) * 4 * n, ctx->stream));
+        MCG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2 * sizeof(int), ctx->stream));
+        PathArgs a;
+        a.indptr = d_indptr;
+        a.indices = d_indices;
+        a.visited = reinterpret_cast<uint32_t *>(d_work);
+        a.front_a = a.visited + n;
+        a.front_b = a.front_a + n;
+        a.next = a.front_b + n;
+        a.list_a = d_work + 4 * n;
+        a.list_b = a.list_a + n;
+        a.counts = d_counts;
+        a.tslot = d_tslot;
+        a.sources = d_sources + s0;
+        a.ns = static_cast<int>(ns - s0 < 32 ? ns - s0 : 32);
+        a.nt = nt;
+        a.out = d_out + s0 * nt;
+        void *params[] = {&a};
+        MCG_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(path_lengths_kernel),
+                                                  dim3(ctx->sm_count * blocks_per_sm), dim3(256),
+                                                  params, 0, ctx->stream));
+        ctx->launches++;
+    }
+    return MCG_OK;
+}

@@ -29,42 +29,9 @@ class DataWrap:
         return (self.data[3], self.data[4]) < (other.data[3], other.data[4])
 
 
-# ---- assembly graph as CSR -----------------------------------------------------------------
-class _GraphCache:
-    """CSR copy of the duck-typed assembly graph (``neighbors(v, mode="ALL")``), built once
-    per graph object; neighbour order is kept as the graph reports it."""
-
-    def __init__(self):
-        self.key = None
-        self.indptr = self.indices = None
-
-    def get(self, assembly_graph, n_vertices):
-        key = (id(assembly_graph), n_vertices)
-        if key != self.key:
-            indptr = np.zeros(n_vertices + 1, dtype=np.int64)
-            chunks = []
-            for v in range(n_vertices):
-                nb = assembly_graph.neighbors(v, mode="ALL")
-                indptr[v + 1] = indptr[v] + len(nb)
-                chunks.append(np.asarray(nb, dtype=np.int32))
-            self.indices = (np.concatenate(chunks) if chunks and indptr[-1] > 0
-                            else np.zeros(0, dtype=np.int32))
-            self.indptr = indptr
-            self.key = key
-        return self.indptr, self.indices
-
-
-_graphs = _GraphCache()
-
-
-def _vertex_count(assembly_graph, *dicts):
-    if hasattr(assembly_graph, "vcount"):
-        return int(assembly_graph.vcount())
-    n = 0
-    for d in dicts:
-        if len(d):
-            n = max(n, max(d) + 1)
-    return n
+# ---- assembly graph as CSR (shared with matching_utils) ----------------------------------------
+_graphs = _backend.graphs
+_vertex_count = _backend.vertex_count
 
 
 class _SeedScores:

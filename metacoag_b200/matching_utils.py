@@ -73,6 +73,45 @@ def _path_len_sum(assembly_graph, contig, bin_members):
     return total
 
 
+class _PathLengths:
+    """The ``len(get_shortest_paths(v, to=w)[0])`` values one marker-gene iteration can ask
+    for (:191-197, :285-292), from one batched multi-source BFS (mcg_path_lengths) over the
+    CSR copy of the assembly graph: sources are the contigs to bin, targets every binned
+    contig plus the contigs that may join a bin during the iteration.  A graph object without
+    ``neighbors`` falls back to the reference's per-pair calls."""
+
+    def __init__(self, assembly_graph, sources, bins, contig_lengths):
+        self.graph = assembly_graph
+        self.table = None
+        if not hasattr(assembly_graph, "neighbors") or len(sources) == 0:
+            return
+        targets = []
+        seen = set()
+        for b in bins:
+            for c in bins[b]:
+                if c not in seen:
+                    seen.add(c)
+                    targets.append(c)
+        for c in sources:
+            if c not in seen:
+                seen.add(c)
+                targets.append(c)
+        n_vertices = _backend.vertex_count(assembly_graph, contig_lengths)
+        n_vertices = max([n_vertices] + [t + 1 for t in targets])
+        indptr, indices = _backend.graphs.get(assembly_graph, n_vertices)
+        self.row = {c: i for i, c in enumerate(sources)}
+        self.col = {c: j for j, c in enumerate(targets)}
+        self.table = _backend.backend().path_lengths(indptr, indices,
+                                                     np.asarray(sources, dtype=np.int64),
+                                                     np.asarray(targets, dtype=np.int64))
+
+    def total(self, contig, bin_members):
+        if self.table is None or contig not in self.row or any(m not in self.col for m in bin_members):
+            return _path_len_sum(self.graph, contig, bin_members)
+        row = self.table[self.row[contig]]
+        return int(sum(int(row[self.col[m]]) for m in bin_members))
+
+
 def match_contigs(smg_iteration, bins, n_bins, bin_of_contig, binned_contigs_with_markers,
                   bin_markers, contig_markers, contig_lengths, contig_names,
                   normalized_tetramer_profiles, coverages, assembly_graph, w_intra, w_inter,
@@ -117,6 +156,7 @@ def match_contigs(smg_iteration, bins, n_bins, bin_of_contig, binned_contigs_wit
             if len(top_nodes) > 0:
                 matching = nx.algorithms.bipartite.matching.minimum_weight_full_matching(
                     graph, top_nodes, "weight")
+                paths = _PathLengths(assembly_graph, to_bin, bins, contig_lengths)
 
                 rejected = {}     # contig -> (seed it was matched to, bin)
                 for seed in matching:
@@ -126,8 +166,7 @@ def match_contigs(smg_iteration, bins, n_bins, bin_of_contig, binned_contigs_wit
                     contig = matching[seed]
                     if contig in bins[b] or (seed, contig) not in edge_weights:
                         continue
-                    avg_path_len = math.floor(
-                        _path_len_sum(assembly_graph, contig, bins[b]) / len(bins[b]))
+                    avg_path_len = math.floor(paths.total(contig, bins[b]) / len(bins[b]))
                     accepted = False
                     if edge_weights[(seed, contig)] <= w_intra and avg_path_len <= d_limit:
                         if len(set(bin_markers[b]).intersection(set(contig_markers[contig]))) == 0:
@@ -154,7 +193,7 @@ def match_contigs(smg_iteration, bins, n_bins, bin_of_contig, binned_contigs_wit
 
                 if chosen != -1:
                     old_bin = rejected[chosen][1]
-                    path_len_sum = _path_len_sum(assembly_graph, chosen, bins[old_bin])
+                    path_len_sum = paths.total(chosen, bins[old_bin])
                     avg_path_len = path_len_sum / len(bins[old_bin])
                     if math.floor(avg_path_len) >= d_limit or path_len_sum == 0:
                         logger.debug("Creating new bin...")

@@ -77,6 +77,24 @@ class OracleBackend:
                 node[i, j], bin_[i, j], depth[i, j] = v, b, d
         return node, bin_, depth, np.array([len(h) for h in hits], dtype=np.int32)
 
+    def path_lengths(self, indptr, indices, sources, targets):
+        out = np.zeros((len(sources), len(targets)), dtype=np.int32)
+        for i, s in enumerate(sources):
+            dist = {int(s): 1}
+            frontier = [int(s)]
+            while frontier:
+                nxt = []
+                for v in frontier:
+                    for u in indices[indptr[v]:indptr[v + 1]]:
+                        u = int(u)
+                        if u not in dist:
+                            dist[u] = dist[v] + 1
+                            nxt.append(u)
+                frontier = nxt
+            for j, t in enumerate(targets):
+                out[i, j] = dist.get(int(t), 0)
+        return out
+
     def normpdf(self, x, mean, sd):
         return np.array([oracle.normpdf(v, mean, sd) for v in np.atleast_1d(x)])
 

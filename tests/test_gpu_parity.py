@@ -14,6 +14,8 @@ import pytest
 from metacoag_b200 import _lib, synth
 from oracle import oracle
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 MAXW = sys.float_info.max
@@ -394,3 +396,44 @@ def test_bfs_depth_overwrite_quirk(ctx):
     got = [(int(node[0, h]), int(depth[0, h])) for h in range(n_hits[0])]
     assert got == [(v, d) for v, _, d in _ref_bfs(0, 10, labels, indptr, indices)]
     assert got[0] == (2, 2)      # distance-1 node reported at depth 2
+
+
+# ---- shortest-path lengths (graph gate of match_contigs) -------------------------------------
+def _csr(n, edges):
+    adj = [set() for _ in range(n)]
+    for a, b in edges:
+        if a != b:
+            adj[a].add(b)
+            adj[b].add(a)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    for v in range(n):
+        indptr[v + 1] = indptr[v] + len(adj[v])
+    indices = np.array([u for v in range(n) for u in sorted(adj[v])], dtype=np.int32)
+    return indptr, indices
+
+
+@pytest.mark.parametrize("kind", ["sparse", "chain", "star"])
+def test_path_lengths_vs_bfs(ctx, kind):
+    """matching_utils.py:191-197: len(get_shortest_paths(v, to=w)[0]) for all pairs -- more than
+    32 sources (two passes), repeated sources and targets, unreachable components, v == w."""
+    from oracle_backend import OracleBackend
+    rng = np.random.default_rng({"sparse": 1, "chain": 2, "star": 3}[kind])
+    if kind == "sparse":
+        n = 3000
+        edges = [(i, i + 1) for i in range(0, 2000)] + \
+            [tuple(rng.integers(0, 2400, 2)) for _ in range(700)]       # 2400.. are isolated
+    elif kind == "chain":
+        n = 20000
+        edges = [(i, i + 1) for i in range(n - 1)]                      # 20 000 levels
+    else:
+        n = 5000
+        edges = [(0, i) for i in range(1, 4000)] + [(i, i + 1) for i in range(4000, 4990)]
+    indptr, indices = _csr(n, edges)
+    sources = rng.integers(0, n, 70)
+    sources[5] = sources[6]
+    targets = np.concatenate([rng.integers(0, n, 300), sources[:10], [0, n - 1]])
+    targets[3] = targets[4]
+    got = ctx.path_lengths(indptr, indices, sources, targets)
+    want = OracleBackend().path_lengths(indptr, indices, sources, targets)
+    assert np.array_equal(got, want)
+    assert (got == 0).any() or kind == "chain"
