@@ -1035,7 +1035,7 @@ extern "C" int mcg_path_lengths(mcg_ctx *ctx, const int64_t *indptr, const int32
     PL_TRY(mcg_reserve(ctx, d_indices, sizeof(int32_t) * std::max<int64_t>(n_edges, 1)));
     PL_TRY(mcg_reserve(ctx, d_tslot, sizeof(int32_t) * n_vertices));
     PL_TRY(mcg_reserve(ctx, d_sources, sizeof(int64_t) * n_sources));
-    PL_TRY(mcg_reserve(ctx, d_work, sizeof(int32_t) * 6 * n_vertices));
+    PL_TRY(mcg_reserve(ctx, d_work, sizeof(int32_t) * (4 * mcg_path_words(n_sources) + 3) * n_vertices));
     PL_TRY(mcg_reserve(ctx, d_counts, 2 * sizeof(int)));
     PL_TRY(mcg_reserve(ctx, d_out, sizeof(int32_t) * n_sources * n_cols));
     PL_TRY(h2d(ctx, d_indptr.p, indptr, sizeof(int64_t) * (n_vertices + 1)));

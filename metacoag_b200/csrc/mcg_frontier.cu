@@ -122,11 +122,12 @@ int mcg_k_bfs(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices, i
 //   number of VERTICES on a shortest path (1 when v == w), 0 when w cannot be reached.  igraph
 //   runs one BFS per (v, w) pair.
 //
-// Here up to 32 sources advance together, one bit each (bit-parallel multi-source BFS): a
-// vertex carries the mask of sources that have reached it, a level expands only the vertices
-// whose mask grew (compact frontier lists, so a level costs its frontier, not the graph), and
-// the first time bit s arrives at a target vertex the pair (s, target) gets level + 1 vertices.
-// One cooperative launch walks all levels with two grid-wide barriers per level.
+// Here all sources of a launch advance together, one bit each (bit-parallel multi-source BFS,
+// W 32-bit words per vertex): a vertex carries the mask of sources that have reached it, a
+// level expands only the vertices whose mask grew (compact frontier lists, so a level costs
+// its frontier, not the graph), and the first time bit s arrives at a target vertex the pair
+// (s, target) gets level + 1 vertices.  One cooperative launch walks all levels with two
+// grid-wide barriers per level, whatever the number of sources.
 #include <cooperative_groups.h>
 
 namespace {
@@ -135,12 +136,13 @@ namespace cg = cooperative_groups;
 struct PathArgs {
     const int64_t *indptr;
     const int32_t *indices;
-    uint32_t *visited, *front_a, *front_b, *next;   // [n] source masks, zero on entry
+    uint32_t *visited, *front_a, *front_b, *next;   // [n, W] source masks, zero on entry
+    int32_t *mark;                                  // [n] level at which the vertex was listed
     int32_t *list_a, *list_b;                       // [n] frontier vertex lists
     int *counts;                                    // [2] list lengths, zero on entry
     const int32_t *tslot;                           // [n] column of the vertex in `out`, or -1
-    const int64_t *sources;                         // [ns] (ns <= 32)
-    int ns;
+    const int64_t *sources;                         // [ns] (ns <= 32 W)
+    int ns, W;
     long long nt;
     int32_t *out;                                   // [ns, nt], zero on entry
 };
@@ -149,13 +151,16 @@ __global__ void __launch_bounds__(256) path_lengths_kernel(PathArgs a) {
     cg::grid_group grid = cg::this_grid();
     const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int W = a.W;
 
     if (tid < a.ns) {
-        const int s = static_cast<int>(a.sources[tid]);
-        const uint32_t bit = 1u << tid;
-        const uint32_t old = atomicOr(&a.visited[s], bit);
-        atomicOr(&a.front_a[s], bit);
-        if (old == 0) a.list_a[atomicAdd(&a.counts[0], 1)] = s;   // the same vertex may be listed as two sources
+        const long long s = a.sources[tid];
+        const uint32_t bit = 1u << (tid & 31);
+        const int w = static_cast<int>(tid >> 5);
+        atomicOr(&a.visited[s * W + w], bit);
+        atomicOr(&a.front_a[s * W + w], bit);
+        // (the same vertex may be given as several sources: it is listed once)
+        if (atomicExch(&a.mark[s], -1) != -1) a.list_a[atomicAdd(&a.counts[0], 1)] = static_cast<int>(s);
         const int col = a.tslot[s];
         if (col >= 0) a.out[tid * a.nt + col] = 1;
     }
@@ -169,15 +174,19 @@ __global__ void __launch_bounds__(256) path_lengths_kernel(PathArgs a) {
         if (n_cur == 0) break;
         // expand: offer this level's new bits to the neighbours that do not have them yet
         for (long long i = tid; i < n_cur; i += stride) {
-            const int v = list_cur[i];
-            const uint32_t f = front_cur[v];
+            const long long v = list_cur[i];
             for (int64_t e = a.indptr[v]; e < a.indptr[v + 1]; ++e) {
-                const int u = a.indices[e];
-                const uint32_t nw = f & ~a.visited[u];
-                if (nw) {
-                    const uint32_t old = atomicOr(&a.next[u], nw);
-                    if (old == 0) list_new[atomicAdd(&a.counts[cur ^ 1], 1)] = u;
+                const long long u = a.indices[e];
+                bool any = false;
+                for (int w = 0; w < W; ++w) {
+                    const uint32_t nw = front_cur[v * W + w] & ~a.visited[u * W + w];
+                    if (nw) {
+                        atomicOr(&a.next[u * W + w], nw);
+                        any = true;
+                    }
                 }
+                if (any && atomicExch(&a.mark[u], level) != level)
+                    list_new[atomicAdd(&a.counts[cur ^ 1], 1)] = static_cast<int>(u);
             }
         }
         grid.sync();
@@ -187,17 +196,22 @@ __global__ void __launch_bounds__(256) path_lengths_kernel(PathArgs a) {
         // commit: the offered bits are all new (visited did not change during the expansion)
         const int n_new = a.counts[cur ^ 1];
         for (long long i = tid; i < n_new; i += stride) {
-            const int u = list_new[i];
-            const uint32_t nx = a.next[u];
-            a.next[u] = 0;
-            a.visited[u] |= nx;
-            front_new[u] = nx;
+            const long long u = list_new[i];
             const int col = a.tslot[u];
-            if (col >= 0)
-                for (uint32_t m = nx; m; m &= m - 1)
-                    a.out[static_cast<long long>(__ffs(m) - 1) * a.nt + col] = level + 1;
+            for (int w = 0; w < W; ++w) {
+                const uint32_t nx = a.next[u * W + w];
+                a.next[u * W + w] = 0;
+                a.visited[u * W + w] |= nx;
+                front_new[u * W + w] = nx;
+                if (col >= 0)
+                    for (uint32_t m = nx; m; m &= m - 1)
+                        a.out[static_cast<long long>(32 * w + __ffs(m) - 1) * a.nt + col] = level + 1;
+            }
         }
-        for (long long i = tid; i < n_cur; i += stride) front_cur[list_cur[i]] = 0;
+        for (long long i = tid; i < n_cur; i += stride) {
+            const long long v = list_cur[i];
+            for (int w = 0; w < W; ++w) front_cur[v * W + w] = 0;
+        }
         grid.sync();
         cur ^= 1;
         uint32_t *tf = front_cur; front_cur = front_new; front_new = tf;
@@ -207,8 +221,16 @@ __global__ void __launch_bounds__(256) path_lengths_kernel(PathArgs a) {
 
 }  // namespace
 
-// d_work: 7 * n_vertices int32 (zeroed here); d_out [ns, nt] int32.  ns may exceed 32: the
-// sources go in groups of 32.
+// d_work: path_work_words(W) * n_vertices int32 for the W this call picks (see
+// mcg_path_words); d_out [ns, nt] int32.  More sources than 32 W go in several launches.
+// Measured (100 k vertices, 200 sources): W = 7 in one launch took 508 ms against 46 ms for seven
+// launches of W = 1 -- a vertex re-enters the frontier once per arrival level of any source,
+// and with W words every entry walks all W of them; the barriers were never the cost.
+int mcg_path_words(int64_t ns) {
+    (void)ns;
+    return 1;
+}
+
 int mcg_k_path_lengths(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
                        int64_t n_vertices, const int32_t *d_tslot, const int64_t *d_sources,
                        int64_t ns, int64_t nt, int32_t *d_work, int *d_counts, int32_t *d_out) {
@@ -224,23 +246,26 @@ int mcg_k_path_lengths(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_i
         if (blocks_per_sm > 4) blocks_per_sm = 4;
     }
     MCG_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int32_t) * ns * nt, ctx->stream));
+    const int W = mcg_path_words(ns);
     const size_t n = static_cast<size_t>(n_vertices);
-    for (int64_t s0 = 0; s0 < ns; s0 += 32) {
-        MCG_CUDA(ctx, cudaMemsetAsync(d_work, 0, sizeof(int32_t) * 4 * n, ctx->stream));
+    for (int64_t s0 = 0; s0 < ns; s0 += 32LL * W) {
+        MCG_CUDA(ctx, cudaMemsetAsync(d_work, 0, sizeof(int32_t) * (4 * W + 1) * n, ctx->stream));
         MCG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2 * sizeof(int), ctx->stream));
         PathArgs a;
         a.indptr = d_indptr;
         a.indices = d_indices;
         a.visited = reinterpret_cast<uint32_t *>(d_work);
-        a.front_a = a.visited + n;
-        a.front_b = a.front_a + n;
-        a.next = a.front_b + n;
-        a.list_a = d_work + 4 * n;
+        a.front_a = a.visited + n * W;
+        a.front_b = a.front_a + n * W;
+        a.next = a.front_b + n * W;
+        a.mark = d_work + 4 * n * W;
+        a.list_a = a.mark + n;
         a.list_b = a.list_a + n;
         a.counts = d_counts;
         a.tslot = d_tslot;
         a.sources = d_sources + s0;
-        a.ns = static_cast<int>(ns - s0 < 32 ? ns - s0 : 32);
+        a.ns = static_cast<int>(ns - s0 < 32LL * W ? ns - s0 : 32LL * W);
+        a.W = W;
         a.nt = nt;
         a.out = d_out + s0 * nt;
         void *params[] = {&a};

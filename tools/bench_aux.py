@@ -1,0 +1,144 @@
+#!/usr/bin/env python3
+"""Measurements of the rows next to the hot path: the graph gate of
+match_contigs, the bin x bin merge matrix, the FASTA reader.  Prints one JSON object.
+
+    python tools/bench_aux.py            (needs a B200; the CPU side is timed in the same run)
+
+CPU comparisons restate what the reference does per call: one BFS per (source, target) pair
+(igraph get_shortest_paths, here a plain-Python BFS over the same CSR -- igraph itself is not
+installed), one get_*_probability triple per bin pair (oracle port), a Python FASTA parser.
+"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from metacoag_b200 import _lib, feature_utils, synth  # noqa: E402
+
+
+def graph(n, seed):
+    """Per-genome chains + chords + a few cross edges, as CSR."""
+    rng = np.random.default_rng(seed)
+    genome = rng.integers(0, 200, n)
+    order = np.argsort(genome, kind="stable")
+    a = order[:-1]
+    b = order[1:]
+    same = genome[a] == genome[b]
+    edges = [np.stack([a[same], b[same]], 1)]
+    chords = rng.integers(0, n, (n // 4, 2))
+    chords = chords[genome[chords[:, 0]] == genome[chords[:, 1]]]
+    cross = rng.integers(0, n, (n // 50, 2))
+    e = np.concatenate(edges + [chords, cross])
+    e = e[e[:, 0] != e[:, 1]]
+    e = np.unique(np.concatenate([e, e[:, ::-1]]), axis=0)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(indptr, e[:, 0] + 1, 1)
+    np.cumsum(indptr, out=indptr)
+    return indptr, e[:, 1].astype(np.int32)
+
+
+def bfs_pair(indptr, indices, s, t):
+    """One (source, target) query the way the reference asks igraph: BFS until t is found."""
+    if s == t:
+        return 1
+    dist = {s: 1}
+    frontier = [s]
+    while frontier:
+        nxt = []
+        for v in frontier:
+            for u in indices[indptr[v]:indptr[v + 1]]:
+                u = int(u)
+                if u not in dist:
+                    dist[u] = dist[v] + 1
+                    if u == t:
+                        return dist[u]
+                    nxt.append(u)
+        frontier = nxt
+    return 0
+
+
+def main():
+    out = {}
+    ctx = _lib.Context(0)
+
+    # ---- graph gate ------------------------------------------------------------------------
+    n = 100000
+    indptr, indices = graph(n, 5)
+    rng = np.random.default_rng(6)
+    sources = rng.choice(n, 200, replace=False)
+    targets = rng.choice(n, 2000, replace=False)
+    ctx.path_lengths(indptr, indices, sources[:4], targets[:4])
+    t0 = time.perf_counter()
+    got = ctx.path_lengths(indptr, indices, sources, targets)
+    gpu_s = time.perf_counter() - t0
+    sample = [(int(rng.integers(0, 200)), int(rng.integers(0, 2000))) for _ in range(60)]
+    t0 = time.perf_counter()
+    for i, j in sample:
+        assert bfs_pair(indptr, indices, int(sources[i]), int(targets[j])) == got[i, j]
+    cpu_s = (time.perf_counter() - t0) / len(sample)
+    out["path_lengths"] = {"vertices": n, "edges": int(indices.shape[0]) // 2, "sources": 200,
+                           "targets": 2000, "gpu_ms_total_incl_copies": gpu_s * 1e3,
+                           "gpu_us_per_pair": gpu_s * 1e6 / 4e5,
+                           "cpu_ms_per_pair_python_bfs": cpu_s * 1e3,
+                           "levels": int(got.max()), "unreachable_pairs": int((got == 0).sum())}
+
+    # ---- bin x bin merge matrix --------------------------------------------------------------------
+    from oracle import oracle
+    for B, S in ((200, 10), (1000, 100)):
+        asm = synth.make_assembly(seed=B, n_genomes=B, n_contigs=B, n_samples=S,
+                                  length_kind="spades", with_graph=False, with_markers=False)
+        _, prof = oracle.count_kmers_batch(asm.blob, asm.offsets, nthreads=0)
+        cov = np.maximum(asm.coverage, 1e-4)
+        ctx.set_profiles(prof)
+        ctx.load_coverage(cov)
+        ids = np.arange(B, dtype=np.int64)
+        ctx.pair_scores(ids[:8], ids[:8], want=("lp",))
+        t0 = time.perf_counter()
+        lp = ctx.pair_scores(ids, ids, want=("pc", "lp"))["lp"]
+        gpu_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        k = 0
+        for i in range(0, B, max(1, B // 20)):
+            for j in range(0, B, max(1, B // 20)):
+                want = oracle.pair_lp(prof[i], prof[j], cov[i], cov[j])[1]
+                assert want == lp[i, j] or abs(want - lp[i, j]) <= 1e-9 * abs(want)
+                k += 1
+        cpu_s = (time.perf_counter() - t0) / k
+        out["merge_matrix_B%d_S%d" % (B, S)] = {
+            "pairs": B * B, "gpu_ms_total_incl_copies": gpu_s * 1e3,
+            "gpu_ns_per_pair": gpu_s * 1e9 / (B * B), "cpu_us_per_pair_c_port": cpu_s * 1e6}
+
+    # ---- FASTA reader ---------------------------------------------------------------------------------
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "contigs.fasta")
+        asm = synth.make_assembly(seed=9, n_genomes=50, n_contigs=20000, n_samples=2,
+                                  length_kind="spades", with_graph=False, with_markers=False)
+        with open(path, "wb") as fh:
+            for i in range(asm.n_contigs):
+                s = asm.blob[asm.offsets[i]:asm.offsets[i + 1]]
+                fh.write(b">NODE_%d_length_%d\n" % (i + 1, s.shape[0]))
+                fh.write(b"\n".join(s[k:k + 60].tobytes() for k in range(0, s.shape[0], 60)) + b"\n")
+        size = os.path.getsize(path)
+        _lib.read_fasta(path, pinned=True)
+        t0 = time.perf_counter()
+        names, blob, offsets = _lib.read_fasta(path, pinned=True)
+        nat = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        recs = list(feature_utils._fasta_records(path))
+        b2, o2 = feature_utils._ascii_blob([r[1] for r in recs])
+        py = time.perf_counter() - t0
+        assert np.array_equal(blob, b2) and np.array_equal(offsets, o2)
+        out["fasta_reader"] = {"file_mb": size / 1e6, "native_s": nat, "native_gb_s": size / nat / 1e9,
+                               "python_parse_and_join_s": py, "speedup": py / nat}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
