@@ -354,20 +354,6 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
             if (range.compare_exchange_weak(v, (k << 32) | e, std::memory_order_acq_rel)) return true;
         }
     };
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
-        pool.emplace_back([&]() {
-            for (;;) {
-                const int64_t k = claim_back();
-                if (k < 0) break;
-                mcg_hostpack_range(bases, offsets, chunks[k].c0, chunks[k].c1, &meta[0].pk_word,
-                                   sizeof(ContigMeta), stage, -1);
-                ready[ready_tail.fetch_add(1, std::memory_order_relaxed)].store(
-                    k, std::memory_order_release);
-            }
-            workers_left.fetch_sub(1, std::memory_order_release);
-        });
-
     int rc = MCG_OK;
     int64_t h2d_bytes = 0, host_bases = 0, gpu_bases = 0;
     int inflight[2] = {-1, -1};          // copy_ev slots of the ASCII runs on the wire
@@ -376,14 +362,9 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
         *w0 = meta[ch.c0].pk_word;
         *w1 = ch.c1 < n ? meta[ch.c1].pk_word : n_words;
     };
-    // host-packed chunks complete roughly from the back; they are copied as runs that end at
-    // `up_hi`, the highest chunk not yet copied
-    std::vector<char> packed_done(static_cast<size_t>(n_chunks), 0);
-    int64_t ready_head = 0, up_hi = n_chunks - 1;
-    for (bool done = false; !done && rc == MCG_OK;) {
-        bool progressed = false;
-        for (int &f : inflight)   // retire ASCII copies that have left
-            if (f >= 0 && cudaEventQuery(ctx->copy_ev[f]) != cudaErrorNotReady) { f = -1; progressed = true; }
+    // hands the copy engine the next ASCII runs from the front while it has a free slot
+    auto feed_copy_engine = [&]() -> bool {
+        bool fed = false;
         for (int &f : inflight) {   // next ASCII run from the front
             if (f >= 0) continue;
             Chunk ch;
@@ -409,8 +390,36 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
             slot = (slot + 1) & 3;
             h2d_bytes += static_cast<int64_t>(bytes);
             gpu_bases += static_cast<int64_t>(bytes);
-            progressed = true;
+            fed = true;
         }
+        return fed;
+    };
+    // the copy engine starts on the front before the pack threads are even created
+    feed_copy_engine();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const int64_t k = claim_back();
+                if (k < 0) break;
+                mcg_hostpack_range(bases, offsets, chunks[k].c0, chunks[k].c1, &meta[0].pk_word,
+                                   sizeof(ContigMeta), stage, -1);
+                ready[ready_tail.fetch_add(1, std::memory_order_relaxed)].store(
+                    k, std::memory_order_release);
+            }
+            workers_left.fetch_sub(1, std::memory_order_release);
+        });
+
+    // host-packed chunks complete roughly from the back; they are copied as runs that end at
+    // `up_hi`, the highest chunk not yet copied
+    std::vector<char> packed_done(static_cast<size_t>(n_chunks), 0);
+    int64_t ready_head = 0, up_hi = n_chunks - 1;
+    for (bool done = false; !done && rc == MCG_OK;) {
+        bool progressed = false;
+        for (int &f : inflight)   // retire ASCII copies that have left
+            if (f >= 0 && cudaEventQuery(ctx->copy_ev[f]) != cudaErrorNotReady) { f = -1; progressed = true; }
+        if (feed_copy_engine()) progressed = true;
+        if (rc != MCG_OK) break;
         // everything claimed and every worker gone: the remaining packed chunks are final
         const bool finishing = workers_left.load(std::memory_order_acquire) == 0 &&
                                (range.load(std::memory_order_acquire) >> 32) >=
