@@ -90,7 +90,7 @@ int mcg_scan(mcg_ctx *ctx);
  * a quarter of their bytes cross the link; the two sides work towards each other, so the
  * split follows their measured speeds, and the packed store is bit-identical either way.
  * threads = 0 turns the host side off; -1 (default) takes MCG_HOST_PACK_THREADS from the
- * environment, else the number of hardware threads.  (Replaces the per-sequence pickling
+ * environment, else the hardware threads minus one (the caller feeds the copy engine).  (Replaces the per-sequence pickling
  * to a worker pool of feature_utils.py:97-104.) */
 int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads);
 /* The host-side packer on its own: ASCII contigs -> the MCG_ENC_2BIT layout described above

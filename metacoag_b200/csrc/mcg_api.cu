@@ -2,7 +2,9 @@
 // points.  The kernels live in mcg_scan.cu, mcg_score.cu and mcg_frontier.cu.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -151,7 +153,7 @@ extern "C" mcg_ctx *mcg_create(int device) {
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->copy2_done, cudaEventDisableTiming);
-    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->copy_start, cudaEventDisableTiming);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i) cudaEventCreate(&ctx->ev[i]);
     if (mcg_reserve(ctx, ctx->status, 4 * sizeof(int32_t)) != MCG_OK) {
@@ -181,7 +183,7 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
     if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
         if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
     if (ctx->copy_start) cudaEventDestroy(ctx->copy_start);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -263,6 +265,17 @@ static int build_layout(mcg_ctx *ctx, const int64_t *offsets, int64_t n,
     return MCG_OK;
 }
 
+// MCG_TRACE=1: host wall-clock marks of the ingest phases on stderr (development aid)
+static double trace_now() {
+    return std::chrono::duration<double, std::milli>(
+               std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static bool trace_on() {
+    static const bool on = getenv("MCG_TRACE") != nullptr;
+    return on;
+}
+#define MCG_MARK(label) do { if (trace_on()) fprintf(stderr, "[mcg] %-22s %.3f ms\n", label, trace_now()); } while (0)
+
 // ---- ASCII ingest: copy engine + GPU pack kernel from the front, host threads + 4x smaller
 // copies from the back ------------------------------------------------------------------------
 extern "C" void mcg_hostpack_range(const uint8_t *bases, const int64_t *offsets, int64_t c0,
@@ -275,7 +288,10 @@ static int host_pack_threads(mcg_ctx *ctx, int64_t n_bases) {
     if (t < 0) {
         const char *env = getenv("MCG_HOST_PACK_THREADS");
         if (env && *env) t = atoi(env);
-        else t = static_cast<int>(std::thread::hardware_concurrency());   // the caller only polls
+        // one core stays with the calling thread: it feeds the copy engine, and when it is
+        // starved by its own workers the split degenerates (measured: 12.3 ms with 15 of 16
+        // threads, 14.5-15 ms with 16)
+        else t = static_cast<int>(std::thread::hardware_concurrency()) - 1;
     }
     return t < 0 ? 0 : (t > 256 ? 256 : t);
 }
@@ -288,8 +304,15 @@ static int host_pack_threads(mcg_ctx *ctx, int64_t n_bases) {
 // stop when they meet, so the split follows the measured speeds of the link and of the host,
 // and the small host chunks keep the tail (workers finishing while the link idles) short.
 // Output is the same packed store either way.
+//
+// `wave` (optional): called on the compute stream's side with a contig range [c0, c1) whose
+// packed words are complete in stream order -- the caller scans and scores it while the rest
+// of the blob is still on its way.  Ranges come from both ends and cover every contig once.
+typedef std::function<int(int64_t, int64_t)> WaveFn;
+
 static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets, int64_t n,
-                        const std::vector<ContigMeta> &meta, int64_t n_words) {
+                        const std::vector<ContigMeta> &meta, int64_t n_words,
+                        const WaveFn *wave = nullptr, int64_t wave_bases = 0) {
     if (n == 0) return MCG_OK;
     const int64_t n_bases = offsets[n];
     const int threads = host_pack_threads(ctx, n_bases);
@@ -356,48 +379,64 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
     };
     int rc = MCG_OK;
     int64_t h2d_bytes = 0, host_bases = 0, gpu_bases = 0;
-    int inflight[2] = {-1, -1};          // copy_ev slots of the ASCII runs on the wire
+    // contigs [front_done, front_c) are packed in stream order but not yet handed to `wave`;
+    // contigs [back_c, back_done) are copied on copy_stream2 but not yet handed to `wave`
+    int64_t front_c = 0, front_done = 0, back_c = n, back_done = n;
+    // The link is one resource: at most kWindow copies (ASCII runs and packed runs together)
+    // are in flight, and packed runs go first -- they carry four times the bases per byte.
+    // Without the shared window the ASCII side kept the copy engine busy on its own and the
+    // packed copies piled up behind it (4.6 ms of drain after the host had finished).
+    constexpr int kWindow = 3;
+    int inflight[kWindow] = {-1, -1, -1};   // copy_ev slots of the copies on the wire
     int slot = 0;
+    auto free_slot = [&]() -> int * {
+        for (int &f : inflight)
+            if (f < 0) return &f;
+        return nullptr;
+    };
     auto word_range = [&](const Chunk &ch, int64_t *w0, int64_t *w1) {
         *w0 = meta[ch.c0].pk_word;
         *w1 = ch.c1 < n ? meta[ch.c1].pk_word : n_words;
     };
-    // hands the copy engine the next ASCII runs from the front while it has a free slot
-    auto feed_copy_engine = [&]() -> bool {
-        bool fed = false;
-        for (int &f : inflight) {   // next ASCII run from the front
-            if (f >= 0) continue;
-            Chunk ch;
-            if (!claim_front_run(&ch)) break;
-            const size_t bytes = static_cast<size_t>(offsets[ch.c1] - offsets[ch.c0]);
-            cudaError_t e = cudaSuccess;
-            if (bytes)
-                e = cudaMemcpyAsync(ctx->ascii.as<uint8_t>() + offsets[ch.c0], bases + offsets[ch.c0],
-                                    bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
-            if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0);
-            if (e != cudaSuccess) {
-                rc = mcg_fail(ctx, MCG_ERR_CUDA, "contig upload failed: %s", cudaGetErrorString(e));
-                break;
-            }
-            int64_t w0, w1;
-            word_range(ch, &w0, &w1);
-            rc = mcg_k_pack_ascii(ctx, ctx->ascii.as<uint8_t>(), ctx->offsets.as<int64_t>(),
-                                  ctx->meta.as<ContigMeta>(), n, w0, w1 - w0,
-                                  ctx->packed.as<uint32_t>());
-            if (rc != MCG_OK) break;
-            f = slot;
-            slot = (slot + 1) & 3;
-            h2d_bytes += static_cast<int64_t>(bytes);
-            gpu_bases += static_cast<int64_t>(bytes);
-            fed = true;
+    // the next ASCII run from the front into a free slot, its pack kernel behind it
+    auto feed_ascii = [&]() -> bool {
+        int *f = free_slot();
+        if (!f) return false;
+        Chunk ch;
+        if (!claim_front_run(&ch)) return false;
+        const size_t bytes = static_cast<size_t>(offsets[ch.c1] - offsets[ch.c0]);
+        cudaError_t e = cudaSuccess;
+        if (bytes)
+            e = cudaMemcpyAsync(ctx->ascii.as<uint8_t>() + offsets[ch.c0], bases + offsets[ch.c0],
+                                bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0);
+        if (e != cudaSuccess) {
+            rc = mcg_fail(ctx, MCG_ERR_CUDA, "contig upload failed: %s", cudaGetErrorString(e));
+            return false;
         }
-        return fed;
+        int64_t w0, w1;
+        word_range(ch, &w0, &w1);
+        rc = mcg_k_pack_ascii(ctx, ctx->ascii.as<uint8_t>(), ctx->offsets.as<int64_t>(),
+                              ctx->meta.as<ContigMeta>(), n, w0, w1 - w0, ctx->packed.as<uint32_t>());
+        if (rc != MCG_OK) return false;
+        *f = slot;
+        slot = (slot + 1) & 7;
+        h2d_bytes += static_cast<int64_t>(bytes);
+        gpu_bases += static_cast<int64_t>(bytes);
+        front_c = ch.c1;
+        if (wave && offsets[front_c] - offsets[front_done] >= wave_bases) {
+            rc = (*wave)(front_done, front_c);
+            front_done = front_c;
+        }
+        return rc == MCG_OK;
     };
     // the copy engine starts on the front before the pack threads are even created
-    feed_copy_engine();
+    MCG_MARK("upload starts");
+    feed_ascii();
+    feed_ascii();
     std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
+    for (int t = 0; t < threads && rc == MCG_OK; ++t)
         pool.emplace_back([&]() {
             for (;;) {
                 const int64_t k = claim_back();
@@ -409,6 +448,7 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
             }
             workers_left.fetch_sub(1, std::memory_order_release);
         });
+    if (static_cast<int>(pool.size()) < threads) workers_left.store(0);
 
     // host-packed chunks complete roughly from the back; they are copied as runs that end at
     // `up_hi`, the highest chunk not yet copied
@@ -416,10 +456,11 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
     int64_t ready_head = 0, up_hi = n_chunks - 1;
     for (bool done = false; !done && rc == MCG_OK;) {
         bool progressed = false;
-        for (int &f : inflight)   // retire ASCII copies that have left
+        bool link_idle = true;
+        for (int &f : inflight) {   // retire the copies that have left
             if (f >= 0 && cudaEventQuery(ctx->copy_ev[f]) != cudaErrorNotReady) { f = -1; progressed = true; }
-        if (feed_copy_engine()) progressed = true;
-        if (rc != MCG_OK) break;
+            if (f >= 0) link_idle = false;
+        }
         // everything claimed and every worker gone: the remaining packed chunks are final
         const bool finishing = workers_left.load(std::memory_order_acquire) == 0 &&
                                (range.load(std::memory_order_acquire) >> 32) >=
@@ -430,36 +471,65 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
             packed_done[k] = 1;
             ++ready_head;
         }
+        // packed runs first
         while (rc == MCG_OK && up_hi >= 0 && packed_done[up_hi]) {
+            int *f = free_slot();
+            if (!f) break;
             int64_t lo = up_hi;
             while (lo > 0 && packed_done[lo - 1]) --lo;
             const Chunk run = {chunks[lo].c0, chunks[up_hi].c1};
             int64_t w0, w1;
             word_range(run, &w0, &w1);
-            if (!finishing && w1 - w0 < packed_copy_words) break;   // let the run grow
+            // small runs wait for their neighbours unless the link has nothing else to do
+            if (!finishing && !link_idle && w1 - w0 < packed_copy_words) break;
             const size_t bytes = sizeof(uint32_t) * static_cast<size_t>(w1 - w0);
-            if (bytes) {
-                cudaError_t e = cudaMemcpyAsync(ctx->packed.as<uint32_t>() + w0, stage + 4 * w0, bytes,
-                                                cudaMemcpyHostToDevice, ctx->copy_stream2);
-                if (e != cudaSuccess)
-                    rc = mcg_fail(ctx, MCG_ERR_CUDA, "packed upload failed: %s", cudaGetErrorString(e));
+            cudaError_t e = cudaSuccess;
+            if (bytes)
+                e = cudaMemcpyAsync(ctx->packed.as<uint32_t>() + w0, stage + 4 * w0, bytes,
+                                    cudaMemcpyHostToDevice, ctx->copy_stream2);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream2);
+            if (e != cudaSuccess) {
+                rc = mcg_fail(ctx, MCG_ERR_CUDA, "packed upload failed: %s", cudaGetErrorString(e));
+                break;
             }
+            const int ev = slot;
+            *f = slot;
+            slot = (slot + 1) & 7;
+            link_idle = false;
             h2d_bytes += static_cast<int64_t>(bytes);
             host_bases += offsets[run.c1] - offsets[run.c0];
             up_hi = lo - 1;
             progressed = true;
+            back_c = run.c0;
+            if (wave && offsets[back_done] - offsets[back_c] >= wave_bases) {
+                e = cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[ev], 0);
+                if (e != cudaSuccess)
+                    rc = mcg_fail(ctx, MCG_ERR_CUDA, "wave sync failed: %s", cudaGetErrorString(e));
+                else
+                    rc = (*wave)(back_c, back_done);
+                back_done = back_c;
+            }
         }
+        // then ASCII into whatever is left of the window
+        while (rc == MCG_OK && feed_ascii()) progressed = true;
         // done: nothing left to claim, workers gone, and every packed chunk handed over (the
         // chunks below up_hi that are not packed_done went to the copy engine as ASCII)
         done = finishing && ready_head == ready_tail.load(std::memory_order_acquire) &&
                (up_hi < 0 || !packed_done[up_hi]);
         if (!progressed && !done) std::this_thread::yield();
     }
+    MCG_MARK("all chunks queued");
     if (rc != MCG_OK) range.store(0);   // let the workers run out of chunks
     for (std::thread &t : pool) t.join();
+    MCG_MARK("workers joined");
     if (rc != MCG_OK) return rc;
     MCG_CUDA(ctx, cudaEventRecord(ctx->copy2_done, ctx->copy_stream2));
     MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy2_done, 0));
+    if (wave) {   // what is left at both ends (the two sides have met: front_c == back_c)
+        if (front_c != back_c) return mcg_fail(ctx, MCG_ERR_STATE, "upload sides did not meet");
+        MCG_TRY((*wave)(front_done, front_c));
+        MCG_TRY((*wave)(back_c, back_done));
+    }
     ctx->ingest_stats[0] = h2d_bytes;
     ctx->ingest_stats[1] = host_bases;
     ctx->ingest_stats[2] = gpu_bases;
@@ -467,8 +537,12 @@ static int upload_ascii(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offse
     return MCG_OK;
 }
 
+// `wave_factory` (optional, ASCII only): given the host layout, returns the function the upload
+// calls for every contig range that has arrived (see upload_ascii).
+typedef std::function<WaveFn(const std::vector<ContigMeta> &, int64_t)> WaveFactory;
+
 static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
-                               int64_t n, int encoding) {
+                               int64_t n, int encoding, const WaveFactory *wave_factory = nullptr) {
     if (n < 0 || (!offsets && n > 0)) return mcg_fail(ctx, MCG_ERR_ARG, "bad contig arguments");
     if (encoding != MCG_ENC_ASCII && encoding != MCG_ENC_2BIT)
         return mcg_fail(ctx, MCG_ERR_ARG, "unknown encoding %d", encoding);
@@ -478,6 +552,7 @@ static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t
     if (n == 0) offsets = zero_off;
     if (offsets[0] != 0) return mcg_fail(ctx, MCG_ERR_ARG, "offsets[0] must be 0");
     MCG_TRY(build_layout(ctx, offsets, n, meta, &n_words, &n_seg));
+    MCG_MARK("layout built");
     const int64_t n_bases = offsets[n] - offsets[0];
     if (n_bases > 0 && !bases) return mcg_fail(ctx, MCG_ERR_ARG, "bases is NULL");
 
@@ -489,25 +564,37 @@ static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t
     {
         TimerScope t(ctx, T_H2D);
         MCG_TRY(h2d(ctx, ctx->meta.p, ctx->pinned, sizeof(ContigMeta) * n));
+        // the words after the last contig are read as halo / by idle lanes
+        MCG_CUDA(ctx, cudaMemsetAsync(ctx->packed.as<uint32_t>() + n_words, 0,
+                                      sizeof(uint32_t) * 32, ctx->stream));
+        MCG_TRY(mcg_k_fill_seg_contig(ctx, ctx->meta.as<ContigMeta>(), n, n_seg,
+                                      ctx->seg_contig.as<int32_t>()));
         if (encoding == MCG_ENC_ASCII) {
             MCG_TRY(mcg_reserve(ctx, ctx->ascii, static_cast<size_t>(n_bases) + 256));
             MCG_TRY(mcg_reserve(ctx, ctx->offsets, sizeof(int64_t) * (n + 1)));
             MCG_TRY(h2d(ctx, ctx->offsets.p, offsets, sizeof(int64_t) * (n + 1)));
-            MCG_TRY(upload_ascii(ctx, bases, offsets, n, meta, n_words));
+            if (wave_factory) {
+                ctx->n_contigs = n;
+                ctx->n_words = n_words;
+                ctx->n_seg = n_seg;
+                ctx->n_bases = n_bases;
+                const WaveFn wave = (*wave_factory)(meta, n_seg);
+                // ~12 waves, none below 32 MB of bases
+                const char *div_env = getenv("MCG_WAVE_DIV");
+                const int64_t div = div_env && atoi(div_env) > 0 ? atoi(div_env) : 12;
+                const int64_t wave_bases = std::max<int64_t>(32 << 20, n_bases / div);
+                MCG_TRY(upload_ascii(ctx, bases, offsets, n, meta, n_words, &wave, wave_bases));
+            } else {
+                MCG_TRY(upload_ascii(ctx, bases, offsets, n, meta, n_words));
+            }
         } else {
             MCG_TRY(h2d(ctx, ctx->packed.p, bases, sizeof(uint32_t) * n_words));
         }
     }
-    // the words after the last contig are read as halo / by idle lanes
-    MCG_CUDA(ctx, cudaMemsetAsync(ctx->packed.as<uint32_t>() + n_words, 0, sizeof(uint32_t) * 32,
-                                  ctx->stream));
-    {
-        TimerScope t(ctx, T_OTHER);
-        MCG_TRY(mcg_k_fill_seg_contig(ctx, ctx->meta.as<ContigMeta>(), n, n_seg,
-                                      ctx->seg_contig.as<int32_t>()));
-    }
     // the pinned meta block must not be overwritten before the copy has left
+    MCG_MARK("before final sync");
     MCG_TRY(sync(ctx));
+    MCG_MARK("after final sync");
     ctx->n_contigs = n;
     ctx->n_words = n_words;
     ctx->n_seg = n_seg;
@@ -1102,7 +1189,9 @@ extern "C" int mcg_get_assignments(mcg_ctx *ctx, int32_t *argmin, double *wmin) 
         if (argmin) MCG_TRY(d2h(ctx, argmin, ctx->argmin.p, sizeof(int32_t) * n));
         if (wmin) MCG_TRY(d2h(ctx, wmin, ctx->wmin.p, sizeof(double) * n));
     }
-    return mcg_check_status(ctx);
+    const int rc_status = mcg_check_status(ctx);
+    MCG_MARK("results on host");
+    return rc_status;
 }
 
 extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int64_t *offsets,
@@ -1111,10 +1200,59 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
                                    int32_t *argmin, double *wmin) {
     MCG_ENTER(ctx);
     if (n <= 0) return mcg_fail(ctx, MCG_ERR_ARG, "no contigs");
+    MCG_MARK("enter");
     MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples));
     MCG_TRY(set_centroids_locked(ctx, cen_prof, cen_cov, n_bins, n_samples));
-    MCG_TRY(load_contigs_locked(ctx, bases, offsets, n, encoding));
-    MCG_TRY(step_locked(ctx, nullptr, nullptr));
+    MCG_MARK("cov+centroids queued");
+    if (encoding == MCG_ENC_ASCII && offsets && offsets[n] >= (64 << 20) && !getenv("MCG_NO_WAVES")) {
+        // Large ASCII loads: every contig range is scanned, normalised and scored as soon as
+        // its packed words are complete in stream order, while the rest is still uploading;
+        // after the last copy only the last range is left to do.
+        MCG_TRY(cov_terms_locked(ctx));
+        MCG_TRY(mcg_reserve(ctx, ctx->counts, sizeof(uint32_t) * MCG_NPROF * n));
+        MCG_TRY(mcg_reserve(ctx, ctx->prof, sizeof(double) * MCG_NPROF * n));
+        MCG_TRY(mcg_reserve(ctx, ctx->prof_norm, sizeof(double) * n));
+        MCG_TRY(mcg_reserve(ctx, ctx->argmin, sizeof(int32_t) * n));
+        MCG_TRY(mcg_reserve(ctx, ctx->wmin, sizeof(double) * n));
+        MCG_CUDA(ctx, cudaMemsetAsync(ctx->counts.p, 0, sizeof(uint32_t) * MCG_NPROF * n, ctx->stream));
+        ctx->n_prof = n;
+        const bool was_profiling = ctx->profiling;
+        const WaveFactory factory = [&](const std::vector<ContigMeta> &meta, int64_t n_seg) -> WaveFn {
+            return [ctx, &meta, n_seg, n](int64_t c0, int64_t c1) -> int {
+                if (c1 <= c0) return MCG_OK;
+                const bool prof = ctx->profiling;
+                ctx->profiling = false;   // one event pair per timer: the waves share T_H2D
+                const int64_t seg0 = meta[c0].seg_first;
+                const int64_t seg1 = c1 < n ? meta[c1].seg_first : n_seg;
+                int rc = mcg_k_scan_range(ctx, ctx->packed.as<uint32_t>(), ctx->meta.as<ContigMeta>(),
+                                          ctx->seg_contig.as<int32_t>(), seg0, seg1,
+                                          ctx->counts.as<uint32_t>());
+                if (rc == MCG_OK)
+                    rc = mcg_k_normalise_norms(ctx, ctx->counts.as<uint32_t>() + c0 * MCG_NPROF,
+                                               ctx->meta.as<ContigMeta>() + c0, c1 - c0,
+                                               ctx->prof.as<double>() + c0 * MCG_NPROF,
+                                               ctx->prof_norm.as<double>() + c0);
+                if (rc == MCG_OK) {
+                    ScoreSide a = contig_side(ctx, nullptr, c1 - c0);
+                    a.first = c0;
+                    ScoreOut out;
+                    out.argmin = ctx->argmin.as<int32_t>() + c0;
+                    out.wmin = ctx->wmin.as<double>() + c0;
+                    rc = mcg_k_pairs(ctx, a, centroid_side(ctx), ctx->n_samples, out,
+                                     ctx->status.as<int32_t>());
+                }
+                ctx->profiling = prof;
+                return rc;
+            };
+        };
+        const int rc = load_contigs_locked(ctx, bases, offsets, n, encoding, &factory);
+        ctx->profiling = was_profiling;
+        MCG_TRY(rc);
+        MCG_MARK("load+waves done");
+    } else {
+        MCG_TRY(load_contigs_locked(ctx, bases, offsets, n, encoding));
+        MCG_TRY(step_locked(ctx, nullptr, nullptr));
+    }
     {
         TimerScope t(ctx, T_D2H);
         if (argmin) MCG_TRY(d2h(ctx, argmin, ctx->argmin.p, sizeof(int32_t) * n));

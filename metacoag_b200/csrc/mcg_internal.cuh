@@ -42,10 +42,10 @@ struct mcg_ctx {
     cudaEvent_t copy2_done = nullptr;
     void *pinned_pack = nullptr;          // host-packed contigs, staged for the copy engine
     size_t pinned_pack_cap = 0;
-    int host_pack_threads = -1;           // -1: MCG_HOST_PACK_THREADS or the hardware threads
+    int host_pack_threads = -1;           // -1: MCG_HOST_PACK_THREADS or the hardware threads - 1
     int64_t ingest_stats[4] = {};         // last ASCII load: h2d bytes, host-packed bases,
                                           // GPU-packed bases, host threads
-    cudaEvent_t copy_ev[4] = {};
+    cudaEvent_t copy_ev[8] = {};
     cudaEvent_t copy_start = nullptr;
     std::mutex mu;
     std::string err;
@@ -142,6 +142,8 @@ int mcg_k_pack_ascii(mcg_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_offs
                      uint32_t *d_packed);
 int mcg_k_fill_seg_contig(mcg_ctx *ctx, const ContigMeta *d_meta, int64_t n_contigs,
                           int64_t n_seg, int32_t *d_seg_contig);
+int mcg_k_scan_range(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d_meta,
+                     const int32_t *d_seg_contig, int64_t seg0, int64_t seg1, uint32_t *d_counts);
 int mcg_k_scan(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d_meta,
                const int32_t *d_seg_contig, int64_t n_seg, int64_t n_contigs,
                uint32_t *d_counts);

@@ -144,8 +144,9 @@ __device__ __forceinline__ void emit_held(uint32_t *__restrict__ counts, int con
 
 __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm)
 scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ meta,
-            const int32_t *__restrict__ seg_contig, long long n_seg,
+            const int32_t *__restrict__ seg_contig, long long seg_base, long long n_seg,
             unsigned long long *__restrict__ tile_counter, uint32_t *__restrict__ counts) {
+    // segments [seg_base, n_seg) of the store (a contig range while the rest is still uploading)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
@@ -180,7 +181,7 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[b] = 0;
     int held = -1;
-    const long long n_tiles = (n_seg + 31) >> 5;
+    const long long n_tiles = (n_seg - seg_base + 31) >> 5;
     unsigned long long tile = 0;
     int in_strip = kStrip;
     for (;;) {
@@ -197,7 +198,7 @@ scan_kernel(const uint32_t *__restrict__ packed, const ContigMeta *__restrict__ 
         ++in_strip;
         if (static_cast<long long>(tile) >= n_tiles) break;
 
-        const long long g = static_cast<long long>(tile) * 32 + lane;
+        const long long g = seg_base + static_cast<long long>(tile) * 32 + lane;
         int contig = -1, nwin = 0, k = 0;
         const uint32_t *wp = packed;
         if (g < n_seg) {
@@ -477,13 +478,11 @@ int mcg_k_fill_seg_contig(mcg_ctx *ctx, const ContigMeta *d_meta, int64_t n_cont
     return MCG_OK;
 }
 
-int mcg_k_scan(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d_meta,
-               const int32_t *d_seg_contig, int64_t n_seg, int64_t n_contigs,
-               uint32_t *d_counts) {
+// Segments [seg0, seg1) into counts (which the caller has zeroed).
+int mcg_k_scan_range(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d_meta,
+                     const int32_t *d_seg_contig, int64_t seg0, int64_t seg1, uint32_t *d_counts) {
     MCG_TRY(ensure_canon_table(ctx));
-    MCG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * MCG_NPROF * n_contigs,
-                                  ctx->stream));
-    if (n_seg == 0) return MCG_OK;
+    if (seg1 <= seg0) return MCG_OK;
     MCG_TRY(mcg_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long)));
     MCG_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned long long),
                                   ctx->stream));
@@ -495,15 +494,23 @@ int mcg_k_scan(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d_meta,
                                            static_cast<int>(smem)));
         if (ctx->device < 64) attr_set[ctx->device] = true;
     }
-    const int64_t n_tiles = (n_seg + 31) / 32;
+    const int64_t n_tiles = (seg1 - seg0 + 31) / 32;
     int64_t grid = static_cast<int64_t>(ctx->sm_count) * kScanCtasPerSm;
     const int64_t need = (n_tiles + kScanWarps - 1) / kScanWarps;
     if (grid > need) grid = need;
     scan_kernel<<<static_cast<unsigned>(grid), kScanThreads, smem, ctx->stream>>>(
-        d_packed, d_meta, d_seg_contig, n_seg, ctx->tile_counter.as<unsigned long long>(),
+        d_packed, d_meta, d_seg_contig, seg0, seg1, ctx->tile_counter.as<unsigned long long>(),
         d_counts);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
+}
+
+int mcg_k_scan(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d_meta,
+               const int32_t *d_seg_contig, int64_t n_seg, int64_t n_contigs,
+               uint32_t *d_counts) {
+    MCG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * MCG_NPROF * n_contigs,
+                                  ctx->stream));
+    return mcg_k_scan_range(ctx, d_packed, d_meta, d_seg_contig, 0, n_seg, d_counts);
 }
 
 int mcg_k_normalise(mcg_ctx *ctx, const uint32_t *d_counts, const ContigMeta *d_meta,

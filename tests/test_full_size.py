@@ -90,6 +90,17 @@ def test_config2_full_size():
         arg, w = check_scoring(ctx, tabs, blob, 400, 1)
         # most contigs go back to the genome they were drawn from
         assert (arg == tabs["genome_of"]).mean() > 0.5
+        # the plug-in call from host buffers scans and scores contig ranges while the rest of
+        # the blob is still uploading: same answer, whatever the split and the wave boundaries
+        ctx.load_coverage(tabs["coverage"])
+        cen_prof, cen_cov = ctx.bin_profiles(tabs["members"], tabs["seg"])
+        for threads in (-1, 3, 0):
+            ctx.set_host_pack_threads(threads)
+            arg3, w3 = ctx.featurise_score(blob, tabs["offsets"], tabs["coverage"], cen_prof, cen_cov)
+            assert np.array_equal(arg3, arg) and np.array_equal(w3, w)
+            counts3 = ctx.get_profiles(want_counts=True)[0]
+            assert np.array_equal(counts3.sum(axis=1, dtype=np.int64),
+                                  np.maximum(np.diff(tabs["offsets"]) - 3, 0))
         # the upload split between copy engine and host pack threads changes nothing
         ctx.set_host_pack_threads(0)
         ctx.load_contigs(blob, tabs["offsets"])
