@@ -291,7 +291,13 @@ static int host_pack_threads(mcg_ctx *ctx, int64_t n_bases) {
         // one core stays with the calling thread: it feeds the copy engine, and when it is
         // starved by its own workers the split degenerates (measured: 12.3 ms with 15 of 16
         // threads, 14.5-15 ms with 16)
-        else t = static_cast<int>(std::thread::hardware_concurrency()) - 1;
+        else {
+            // the ranks of one box (torchrun exports LOCAL_WORLD_SIZE) share its cores
+            int local_world = 1;
+            const char *lw = getenv("LOCAL_WORLD_SIZE");
+            if (lw && atoi(lw) > 0) local_world = atoi(lw);
+            t = static_cast<int>(std::thread::hardware_concurrency()) / local_world - 1;
+        }
     }
     return t < 0 ? 0 : (t > 256 ? 256 : t);
 }
