@@ -82,6 +82,7 @@ struct mcg_ctx {
     DevBuf argmin, wmin;       // int32 [n], f64 [n]
     DevBuf status;             // int32 [4] device-side flags (0: domain error)
     DevBuf scratch[6];
+    bool force_split = false;  // rule C always on the two-kernel path (waves: results must not depend on batch size)
     bool redo_valid = false;   // scratch[4] starts with the redo count of the last guarded rule-C call
     void *pinned = nullptr;    // small pinned staging block
     size_t pinned_cap = 0;

@@ -121,6 +121,7 @@ struct MathConst {
     double inv_two_var_intra, inv_denom_intra, inv_two_var_inter, inv_denom_inter, inv_ln10;
     double log_inv_denom_intra;                       // -log(sd_intra * sqrt(2 pi))
     double sd_ratio;                                  // sd_intra / sd_inter
+    double log_sd_ratio;
 };
 __constant__ MathConst c_math;
 
@@ -317,8 +318,19 @@ __device__ __forceinline__ double log_comp_prob_warp(double d2, const double *__
     const double ai = -d2 * c_math.inv_two_var_intra;
     const double ae = -(dx * dx) * c_math.inv_two_var_inter;
     const bool special = !(ai >= -700.0) || !(ae >= -700.0) || !(ai <= 0.0);
-    const double rho = exp_core(special ? 0.0 : ae - ai, etab) * c_math.sd_ratio;
-    double out = -log_normal(1.0 + rho, ltab);
+    // rho > 2^62 once ae - ai > 44: log(1 + rho) and log(rho) = log(sd_i / sd_e) + (ae - ai) are
+    // then the same double.  That is every pair whose profiles are further apart than ~0.05;
+    // a pass whose 32 lanes are all there skips the table exp and log.  A lane takes the
+    // closed form whatever its neighbours do, so a pair's weight does not depend on the batch
+    // it is scored in.
+    const double diff = ae - ai;
+    const bool big = !special && diff > 44.0;
+    double out = -(diff + c_math.log_sd_ratio);
+    if (!__all_sync(0xffffffffu, big || special)) {
+        const double rho = exp_core((special || big) ? 0.0 : diff, etab) * c_math.sd_ratio;
+        const double slow = -log_normal(1.0 + rho, ltab);
+        if (!big) out = slow;
+    }
     if (__any_sync(0xffffffffu, special)) {
         if (special) out = log_comp_prob_special(d, ai, ae, etab, ltab, status);
     }
@@ -1270,6 +1282,7 @@ static int ensure_gauss(mcg_ctx *ctx) {
     m.inv_ln10 = 1.0 / g.ln10;
     m.log_inv_denom_intra = -log(g.denom_intra);
     m.sd_ratio = sd_i / sd_e;
+    m.log_sd_ratio = log(sd_i / sd_e);
     MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_math, &m, sizeof m, 0, cudaMemcpyHostToDevice,
                                           ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1458,7 +1471,7 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
     // big rule-C batches: distance GEMM + probability kernel (argmin/wmin are needed to
     // carry the running minimum when the bins do not fit one shared-memory group)
     // (S > 30: only without the weight matrix -- deferred pairs have no exact weight there)
-    if (rule_c && a.n >= 2048 && out.argmin && out.wmin &&
+    if (rule_c && (a.n >= 2048 || ctx->force_split) && out.argmin && out.wmin &&
         (logsum || (!out.weights && split_fits(n_samples))))
         return split_rule_c(ctx, a, b, n_samples, out, d_status);
     if (out.dist) {
