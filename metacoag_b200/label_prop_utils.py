@@ -73,19 +73,53 @@ def _bfs_hits(nodes, threshold, bin_of_contig, assembly_graph, n_vertices):
             for i in range(starts.shape[0])]
 
 
-def _candidates(nodes, threshold, bin_of_contig, scores, assembly_graph, n_vertices):
-    """``[set of (node, labelled, bin, depth, score)]`` per node, the sets built by inserting
-    the hits in pop order like the reference does (:88-90)."""
-    nodes = list(nodes)
+def _local_candidates(nodes, threshold, bin_of_contig, scores, assembly_graph, n_vertices):
+    """(node, labelled, bin, depth, score) rows of ``nodes``, hits in pop order."""
     hits = _bfs_hits(nodes, threshold, bin_of_contig, assembly_graph, n_vertices)
     scores.ensure(n for n, h in zip(nodes, hits) if h)
-    out = []
+    rows = []
     for n, node_hits in zip(nodes, hits):
-        found = set()
         for labelled, b, d in node_hits:
-            found.add((n, labelled, b, d, scores.get(n, b)))
-        out.append(found)
-    return out
+            rows.append((n, labelled, b, d, scores.get(n, b)))
+    return rows
+
+
+def _distributed_world():
+    """World size when torch.distributed is up (the package does not import torch otherwise)."""
+    import sys
+    if "torch.distributed" not in sys.modules:
+        return 1
+    from . import parallel
+    return parallel.world()
+
+
+def _candidates(nodes, threshold, bin_of_contig, scores, assembly_graph, n_vertices):
+    """``[set of (node, labelled, bin, depth, score)]`` per node, the sets built by inserting
+    the hits in pop order like the reference does (:88-90).  With several ranks
+    (torch.distributed initialised) large batches are sharded: every rank walks and scores a
+    slice of the nodes and the rows are all-gathered (metacoag_b200/parallel.py)."""
+    nodes = list(nodes)
+    if _distributed_world() > 1:
+        from . import parallel
+        if len(nodes) >= parallel.MIN_SHARDED_NODES:
+            lo, hi = parallel.shard_slice(len(nodes))
+            mine = _local_candidates(nodes[lo:hi], threshold, bin_of_contig, scores,
+                                     assembly_graph, n_vertices)
+            ints = np.array([r[:4] for r in mine], dtype=np.int64).reshape(-1, 4)
+            floats = np.array([[r[4]] for r in mine], dtype=np.float64).reshape(-1, 1)
+            ints, floats = parallel.all_gather_rows(ints, floats)
+            rows = [(int(a), int(b), int(c), int(d), float(f[0])) for (a, b, c, d), f
+                    in zip(ints.tolist(), floats.tolist())]
+        else:
+            rows = _local_candidates(nodes, threshold, bin_of_contig, scores, assembly_graph,
+                                     n_vertices)
+    else:
+        rows = _local_candidates(nodes, threshold, bin_of_contig, scores, assembly_graph,
+                                 n_vertices)
+    by_node = {}
+    for row in rows:
+        by_node.setdefault(row[0], set()).add(row)
+    return [by_node.get(n, set()) for n in nodes]
 
 
 def run_bfs_long(node, threhold, binned_contigs, bin_of_contig, bins, smg_bin_counts,

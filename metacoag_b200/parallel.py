@@ -90,3 +90,62 @@ def gather_assignments(argmin, wmin, counts=None):
     keep = torch.cat([torch.arange(r * width, r * width + c, device=argmin.device)
                       for r, c in enumerate(counts)])
     return out_a[keep], out_w[keep]
+
+
+# ---- label propagation: candidate generation sharded over the ranks (SURVEY.md 8e) ---------------
+# The sequential part of label_prop / final_label_prop (heap, marker-gene rules) runs replicated
+# and deterministically on every rank; what is sharded is the batch work in front of it -- the
+# bounded BFS from every unbinned long contig and the rule-B scores of its hits
+# (label_prop_utils.py:24-100).  Every rank takes a contiguous slice of the start nodes and the
+# (node, labelled node, bin, depth, score) rows are all-gathered, so that all ranks hold the
+# same candidate sets, bit for bit, and stay in lock step.
+MIN_SHARDED_NODES = 256     # below this a collective costs more than the work it saves
+stats = {"sharded_calls": 0, "rows_gathered": 0}
+
+
+def world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def shard_slice(n, rank=None, world_size=None):
+    """[lo, hi) of ``n`` items for this rank, contiguous, sizes differing by at most one."""
+    world_size = world() if world_size is None else world_size
+    rank = (dist.get_rank() if world_size > 1 else 0) if rank is None else rank
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _collective_device():
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def all_gather_rows(ints, floats):
+    """All-gather ragged row blocks: ``ints`` int64[k, a] and ``floats`` float64[k, b] of this
+    rank -> the concatenation over ranks, in rank order (numpy in, numpy out)."""
+    dev = _collective_device()
+    ints = np.ascontiguousarray(ints, dtype=np.int64)
+    floats = np.ascontiguousarray(floats, dtype=np.float64)
+    k = ints.shape[0]
+    w = dist.get_world_size()
+    mine = torch.tensor([k], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(mine) for _ in range(w)]
+    dist.all_gather(counts, mine)
+    counts = [int(c.item()) for c in counts]
+    width = max(counts + [1])
+    pad_i = torch.zeros((width, ints.shape[1]), dtype=torch.int64, device=dev)
+    pad_f = torch.zeros((width, floats.shape[1]), dtype=torch.float64, device=dev)
+    if k:
+        pad_i[:k] = torch.from_numpy(ints).to(dev)
+        pad_f[:k] = torch.from_numpy(floats).to(dev)
+    out_i = torch.empty((w * width, ints.shape[1]), dtype=torch.int64, device=dev)
+    out_f = torch.empty((w * width, floats.shape[1]), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out_i, pad_i)
+    dist.all_gather_into_tensor(out_f, pad_f)
+    out_i, out_f = out_i.cpu().numpy(), out_f.cpu().numpy()
+    keep = np.concatenate([np.arange(r * width, r * width + c) for r, c in enumerate(counts)])
+    stats["sharded_calls"] += 1
+    stats["rows_gathered"] += int(keep.shape[0])
+    return out_i[keep], out_f[keep]

@@ -80,3 +80,45 @@ def test_broadcast_and_gather_world2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), 1001, str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+# ---- label propagation with the candidate generation sharded over two ranks ---------------------
+def _label_prop_worker(rank, world, port, golden_dir, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import json
+        import sys
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path.insert(0, here)
+        sys.path.insert(0, os.path.join(here, "golden"))
+        import test_pipeline
+        from oracle_backend import OracleBackend
+        from metacoag_b200 import _backend
+        parallel.MIN_SHARDED_NODES = 2          # the golden assembly is small
+        _backend.set_backend(OracleBackend())
+        states, want = test_pipeline.run(golden_dir, os.path.join(result_dir, "work%d" % rank))
+        test_pipeline.compare(states, want, exact_floats=True)
+        assert parallel.stats["sharded_calls"] > 0 and parallel.stats["rows_gathered"] > 0
+        json.dump({"final": {str(k): v for k, v in states["final_label_prop"].items()},
+                   "sharded_calls": parallel.stats["sharded_calls"]},
+                  open(os.path.join(result_dir, "rank%d.json" % rank), "w"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_label_prop_sharded_candidates_world2(golden_dir, tmp_path):
+    """Both ranks shard the BFS + rule-B work of label_prop / final_label_prop, all-gather the
+    candidate rows and run the sequential part replicated: same bins as the reference after
+    every stage, on both ranks, with the same number of collectives."""
+    import json
+    world = 2
+    for r in range(world):
+        os.makedirs(tmp_path / ("work%d" % r))
+    mp.spawn(_label_prop_worker, args=(world, _free_port(), golden_dir, str(tmp_path)),
+             nprocs=world, join=True)
+    res = [json.load(open(tmp_path / ("rank%d.json" % r))) for r in range(world)]
+    assert res[0]["final"] == res[1]["final"]
+    assert res[0]["sharded_calls"] == res[1]["sharded_calls"] > 0
