@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
