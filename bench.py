@@ -408,16 +408,18 @@ def main():
     scan_roof = roof("scan_kernel", "hbm", scan_bytes, kernel_ms["scan"], hbm_peak, "GB/s", hbm_src,
                      algorithmic_bytes=scan_bytes,
                      gbases_per_s=n_bases / (kernel_ms["scan"] * 1e-3) / 1e9,
-                     note="issue / shared-memory bound by design (DESIGN.md 4.1): ~11 "
-                          "instructions per base against 2 for 70 % of HBM")
+                     note="bound by the L1TEX load/store data pipe, not HBM (DESIGN.md 4.1): two "
+                          "shared-memory wavefronts per 32 windows is the floor of a "
+                          "byte-counter histogram")
     # The scan is not HBM-bound: its counters live in shared memory and every window costs a
-    # byte load and a byte store there.  The crossbar moves one 128-byte wavefront per clock per
-    # SM; the wavefront count per launch comes from the same ncu capture as `traffic`.
-    wf = captured.get(wl_key, {}).get("scan_kernel_smem_wavefronts")
+    # byte load and a byte store there.  What it fills is the L1TEX load/store data pipe, one
+    # 128-byte wavefront per clock per SM (ncu: l1tex__data_pipe_lsu_wavefronts 88 % of peak);
+    # the wavefront count per launch comes from the same ncu capture as `traffic`.
+    wf = captured.get(wl_key, {}).get("scan_kernel_lsu_wavefronts")
     if wf:
         sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
         peak_wf = 148 * sm_clock
-        scan_roof["binding"] = {"resource": "shared-memory crossbar (wavefronts/s)",
+        scan_roof["binding"] = {"resource": "L1TEX LSU data pipe (shared + global wavefronts/s)",
                                 "achieved": wf / (kernel_ms["scan"] * 1e-3), "peak": peak_wf,
                                 "frac": wf / (kernel_ms["scan"] * 1e-3) / peak_wf,
                                 "wavefronts_per_launch": wf,
