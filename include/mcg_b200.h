@@ -189,6 +189,13 @@ int mcg_path_lengths(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices
                      int64_t n_vertices, const int64_t *sources, int64_t n_sources,
                      const int64_t *targets, int64_t n_targets, int32_t *out);
 
+/* graph_utils.py:407-443 get_connected_components / get_non_isolated: the reference grows
+ * the component of every binned contig by repeated neighbour sweeps (quadratic in the
+ * component size, per start vertex).  labels[v] = smallest vertex id of the component of v
+ * over the undirected CSR graph; the host groups vertices by label. */
+int mcg_connected_components(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
+                             int64_t n_vertices, int32_t *labels);
+
 /* ---- fused plug-in call and the resident step ---------------------------------- */
 /* Featurise + score in one call from HOST buffers: upload, pack, scan, normalise,
  * coverage terms, rule-C scoring against the given centroids, download

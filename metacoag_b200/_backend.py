@@ -86,6 +86,11 @@ graphs = GraphCache()
 def vertex_count(assembly_graph, *dicts):
     if hasattr(assembly_graph, "vcount"):
         return int(assembly_graph.vcount())
+    if hasattr(assembly_graph, "vs"):
+        try:
+            return len(assembly_graph.vs)
+        except TypeError:
+            pass
     n = 0
     for d in dicts:
         if len(d):
@@ -174,6 +179,10 @@ class GpuBackend:
     def bfs_candidates(self, indptr, indices, labels, starts, depth_limit):
         with self._lock:
             return self.ctx.bfs_candidates(indptr, indices, labels, starts, depth_limit)
+
+    def connected_components(self, indptr, indices):
+        with self._lock:
+            return self.ctx.connected_components(indptr, indices)
 
     def path_lengths(self, indptr, indices, sources, targets):
         """[len(sources), len(targets)] vertices on a shortest path, 0 = unreachable."""

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mcg_bfs_candidates": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _vp, _vp,
                                   _vp, _vp]),
     "mcg_path_lengths": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "mcg_connected_components": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "mcg_featurise_score": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _i64, _vp,
                                    _vp]),
     "mcg_set_centroids": (_int, [_vp, _vp, _vp, _i64]),
@@ -406,6 +407,15 @@ class Context:
             self.handle, _ptr(indptr), _ptr(indices), indptr.shape[0] - 1, _ptr(sources),
             sources.shape[0], _ptr(targets), targets.shape[0], _ptr(out)))
         return out
+
+    def connected_components(self, indptr, indices):
+        """int32[n]: smallest vertex id of every vertex's component."""
+        indptr = _arr(indptr, np.int64)
+        indices = _arr(indices, np.int32)
+        labels = np.zeros(indptr.shape[0] - 1, dtype=np.int32)
+        self._check(self.lib.mcg_connected_components(self.handle, _ptr(indptr), _ptr(indices),
+                                                      indptr.shape[0] - 1, _ptr(labels)))
+        return labels
 
     # -- fused / resident ---------------------------------------------------------------------
     def featurise_score(self, bases, offsets, cov, cen_prof, cen_cov, encoding=ENC_ASCII,

@@ -1161,6 +1161,43 @@ extern "C" int mcg_path_lengths(mcg_ctx *ctx, const int64_t *indptr, const int32
     return MCG_OK;
 }
 
+extern "C" int mcg_connected_components(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
+                                        int64_t n_vertices, int32_t *labels) {
+    MCG_ENTER(ctx);
+    if (n_vertices < 0 || !indptr || !labels) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    if (n_vertices == 0) return MCG_OK;
+    if (n_vertices > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many vertices");
+    const int64_t n_edges = indptr[n_vertices];
+    if (n_edges > 0 && !indices) return mcg_fail(ctx, MCG_ERR_ARG, "indices is NULL");
+    for (int64_t e = 0; e < n_edges; ++e)
+        if (indices[e] < 0 || indices[e] >= n_vertices)
+            return mcg_fail(ctx, MCG_ERR_ARG, "edge endpoint %d out of range", indices[e]);
+    DevBuf d_indptr, d_indices, d_work, d_flag, d_labels;
+    int rc = MCG_OK;
+    auto cleanup = [&]() {
+        for (DevBuf *b : {&d_indptr, &d_indices, &d_work, &d_flag, &d_labels})
+            if (b->p) cudaFree(b->p);
+    };
+#define CC_TRY(expr) do { rc = (expr); if (rc != MCG_OK) { cleanup(); return rc; } } while (0)
+    CC_TRY(mcg_reserve(ctx, d_indptr, sizeof(int64_t) * (n_vertices + 1)));
+    CC_TRY(mcg_reserve(ctx, d_indices, sizeof(int32_t) * std::max<int64_t>(n_edges, 1)));
+    CC_TRY(mcg_reserve(ctx, d_work, sizeof(int32_t) * 2 * n_vertices));
+    CC_TRY(mcg_reserve(ctx, d_flag, sizeof(int)));
+    CC_TRY(mcg_reserve(ctx, d_labels, sizeof(int32_t) * n_vertices));
+    CC_TRY(h2d(ctx, d_indptr.p, indptr, sizeof(int64_t) * (n_vertices + 1)));
+    if (n_edges) CC_TRY(h2d(ctx, d_indices.p, indices, sizeof(int32_t) * n_edges));
+    {
+        TimerScope t(ctx, T_OTHER);
+        CC_TRY(mcg_k_components(ctx, d_indptr.as<int64_t>(), d_indices.as<int32_t>(), n_vertices,
+                                d_work.as<int32_t>(), d_flag.as<int>(), d_labels.as<int32_t>()));
+    }
+    CC_TRY(d2h(ctx, labels, d_labels.p, sizeof(int32_t) * n_vertices));
+    CC_TRY(sync(ctx));
+    cleanup();
+#undef CC_TRY
+    return MCG_OK;
+}
+
 // ---- fused plug-in call and the resident step ---------------------------------------------------------------------------
 static int step_locked(mcg_ctx *ctx, int32_t *d_argmin, double *d_wmin) {
     if (ctx->n_contigs == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no contigs resident");

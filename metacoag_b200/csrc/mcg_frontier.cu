@@ -276,3 +276,73 @@ int mcg_k_path_lengths(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_i
     }
     return MCG_OK;
 }
+
+// ---- connected components (graph_utils.get_non_isolated) -------------------------------------------
+//
+//   reference: graph_utils.py:407-443 grows, for every binned contig i, the component of i by
+//   repeated neighbour sweeps over a Python list (`neighbour not in component` is a linear scan,
+//   so a component of c vertices costs O(c^2) per start vertex) and hands it to a process pool.
+//
+// Here one labelling of the whole CSR graph (FastSV: stochastic + aggressive hooking onto the
+// grandparent, then shortcutting, all with atomicMin on a double-buffered parent array)
+// gives every vertex the smallest vertex id of its component in O(log n) rounds; the host
+// groups vertices by label.
+namespace {
+
+__global__ void cc_hook_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                               long long n, const int32_t *__restrict__ f, int32_t *__restrict__ fn) {
+    const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (v >= n) return;
+    const int32_t fv = f[v];
+    const int32_t gv = f[fv];
+    atomicMin(&fn[v], gv);                            // shortcutting
+    for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) {
+        const int32_t u = indices[e];
+        const int32_t gu = f[f[u]];
+        atomicMin(&fn[fv], gu);                       // stochastic hooking
+        atomicMin(&fn[v], gu);                        // aggressive hooking
+    }
+}
+
+__global__ void cc_diff_kernel(const int32_t *__restrict__ f, const int32_t *__restrict__ fn,
+                               long long n, int *__restrict__ changed) {
+    const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (v < n && f[v] != fn[v]) *changed = 1;
+}
+
+__global__ void cc_init_kernel(int32_t *__restrict__ f, int32_t *__restrict__ fn, long long n) {
+    const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (v < n) { f[v] = static_cast<int32_t>(v); fn[v] = static_cast<int32_t>(v); }
+}
+
+}  // namespace
+
+// d_work: 2 * n int32; on return d_labels[v] = smallest vertex id of v's component.
+int mcg_k_components(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
+                     int64_t n, int32_t *d_work, int *d_flag, int32_t *d_labels) {
+    if (n == 0) return MCG_OK;
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((n + threads - 1) / threads);
+    int32_t *f = d_work, *fn = d_work + n;
+    cc_init_kernel<<<blocks, threads, 0, ctx->stream>>>(f, fn, n);
+    MCG_KERNEL_CHECK(ctx);
+    for (int round = 0; round < 64; ++round) {
+        cc_hook_kernel<<<blocks, threads, 0, ctx->stream>>>(d_indptr, d_indices, n, f, fn);
+        MCG_KERNEL_CHECK(ctx);
+        MCG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+        cc_diff_kernel<<<blocks, threads, 0, ctx->stream>>>(f, fn, n, d_flag);
+        MCG_KERNEL_CHECK(ctx);
+        int changed = 0;
+        MCG_CUDA(ctx, cudaMemcpyAsync(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MCG_CUDA(ctx, cudaMemcpyAsync(f, fn, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+        if (!changed) {
+            MCG_CUDA(ctx, cudaMemcpyAsync(d_labels, fn, sizeof(int32_t) * n,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+            return MCG_OK;
+        }
+    }
+    return mcg_fail(ctx, MCG_ERR_STATE, "connected components did not converge in 64 rounds");
+}

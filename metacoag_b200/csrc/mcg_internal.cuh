@@ -199,6 +199,8 @@ int mcg_k_bfs(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices, i
               const int32_t *d_labels, const int64_t *d_starts, int64_t n_starts, int depth_limit,
               int max_hits, int32_t *d_hit_node, int32_t *d_hit_bin, int32_t *d_hit_depth,
               int32_t *d_n_hits, int32_t *d_work, int64_t work_stride);
+int mcg_k_components(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
+                     int64_t n, int32_t *d_work, int *d_flag, int32_t *d_labels);
 int mcg_path_words(int64_t ns);   // mask words per vertex; work space = (4 W + 3) n int32
 int mcg_k_path_lengths(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
                        int64_t n_vertices, const int32_t *d_tslot, const int64_t *d_sources,

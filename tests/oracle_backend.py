@@ -77,6 +77,22 @@ class OracleBackend:
                 node[i, j], bin_[i, j], depth[i, j] = v, b, d
         return node, bin_, depth, np.array([len(h) for h in hits], dtype=np.int32)
 
+    def connected_components(self, indptr, indices):
+        n = len(indptr) - 1
+        labels = np.full(n, -1, dtype=np.int32)
+        for s in range(n):
+            if labels[s] >= 0:
+                continue
+            labels[s] = s
+            stack = [s]
+            while stack:
+                v = stack.pop()
+                for u in indices[indptr[v]:indptr[v + 1]]:
+                    if labels[u] < 0:
+                        labels[u] = s
+                        stack.append(int(u))
+        return labels
+
     def path_lengths(self, indptr, indices, sources, targets):
         out = np.zeros((len(sources), len(targets)), dtype=np.int32)
         for i, s in enumerate(sources):
