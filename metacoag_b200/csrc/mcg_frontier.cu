@@ -243,7 +243,9 @@ int mcg_k_path_lengths(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_i
         MCG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm,
                                                                     path_lengths_kernel, 256, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
-        if (blocks_per_sm > 4) blocks_per_sm = 4;
+        // frontiers are thousands of vertices, not millions: more CTAs only make the grid
+        // barrier (two per level) slower
+        if (blocks_per_sm > 1) blocks_per_sm = 1;
     }
     MCG_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int32_t) * ns * nt, ctx->stream));
     const int W = mcg_path_words(ns);
