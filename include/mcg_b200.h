@@ -104,7 +104,8 @@ int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, int64_t n, 
  * names and sequences (BioPython's SimpleFastaParser rules: text before the first '>' skipped,
  * id = first word of the header, lines right-stripped, ' ' removed, "\n" / "\r\n" / "\r" line
  * ends) as one byte blob + offsets, ready for mcg_load_contigs, instead of a list of Python
- * strings.  mcg_fasta_index sizes the outputs; mcg_fasta_load fills caller-owned buffers
+ * strings (the file is cut at record starts and the ranges are parsed in parallel).
+ * mcg_fasta_index sizes the outputs; mcg_fasta_load fills caller-owned buffers
  * (bases[n_bases], offsets[n_records + 1], names[name_bytes], name_offsets[n_records + 1]).
  * Return 0, -1 if the file cannot be read, -2 if it changed between the two calls. */
 int mcg_fasta_index(const char *path, int64_t *n_records, int64_t *n_bases, int64_t *name_bytes);

@@ -161,6 +161,12 @@ extern "C" int mcg_hostpack_level(void) {
 //   The two passes below produce exactly that, as one byte blob + offsets instead of a list of
 //   Python strings: pass 1 sizes the outputs, pass 2 fills caller-owned
 //   (pinned) buffers.
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -244,10 +250,6 @@ template <bool FILL> void fasta_pass(const uint8_t *data, size_t size, FastaOut 
         fasta_line<FILL>(p, e, &in_record, o);
         p = next;
     }
-    if (FILL && o->n_records && !o->overflow) {
-        o->offsets[o->n_records] = o->n_bases;
-        o->name_offsets[o->n_records] = o->name_bytes;
-    }
 }
 
 struct Mapped {
@@ -275,41 +277,110 @@ struct Mapped {
 
 }  // namespace
 
+// Record-aligned byte ranges of the file, one per worker: a range starts at a '>' that opens a
+// line (or at 0).  MCG_FASTA_RANGE_BYTES sets the target size (default 8 MB; the tests use a
+// few bytes to put a boundary at every record).
+static std::vector<size_t> fasta_ranges(const uint8_t *data, size_t size) {
+    size_t target = 8u << 20;
+    if (const char *env = getenv("MCG_FASTA_RANGE_BYTES"))
+        if (atoll(env) > 0) target = static_cast<size_t>(atoll(env));
+    size_t parts = size / target;
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    if (parts > 4 * hw) parts = 4 * hw;
+    std::vector<size_t> cuts{0};
+    for (size_t i = 1; i < parts; ++i) {
+        size_t p = std::max(cuts.back() + 1, size / parts * i);
+        while (p < size && !(data[p] == '>' && (data[p - 1] == '\n' || data[p - 1] == '\r'))) ++p;
+        if (p >= size) break;
+        cuts.push_back(p);
+    }
+    cuts.push_back(size);
+    return cuts;
+}
+
+// Pass 1 over every range in parallel: counts per range.
+static void fasta_count(const uint8_t *data, const std::vector<size_t> &cuts,
+                        std::vector<FastaOut> *per_range) {
+    const size_t n = cuts.size() - 1;
+    per_range->assign(n, FastaOut());
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (size_t i; (i = next.fetch_add(1)) < n;)
+            fasta_pass<false>(data + cuts[i], cuts[i + 1] - cuts[i], &(*per_range)[i]);
+    };
+    const size_t workers = std::min<size_t>(n, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < workers; ++t) pool.emplace_back(work);
+    work();
+    for (std::thread &t : pool) t.join();
+}
+
 // Pass 1.  Returns 0, or -1 when the file cannot be read.
 extern "C" int mcg_fasta_index(const char *path, int64_t *n_records, int64_t *n_bases,
-                                   int64_t *name_bytes) {
+                               int64_t *name_bytes) {
     Mapped m;
     if (!m.open(path)) return -1;
-    FastaOut o;
-    fasta_pass<false>(m.data, m.size, &o);
-    *n_records = o.n_records;
-    *n_bases = o.n_bases;
-    *name_bytes = o.name_bytes;
+    const std::vector<size_t> cuts = fasta_ranges(m.data, m.size);
+    std::vector<FastaOut> per_range;
+    fasta_count(m.data, cuts, &per_range);
+    *n_records = *n_bases = *name_bytes = 0;
+    for (const FastaOut &o : per_range) {
+        *n_records += o.n_records;
+        *n_bases += o.n_bases;
+        *name_bytes += o.name_bytes;
+    }
     return 0;
 }
 
-// Pass 2 into buffers sized by pass 1 (offsets and name_offsets have n_records + 1 entries).
+// Pass 2 into buffers sized by pass 1 (offsets and name_offsets have n_records + 1 entries):
+// the ranges are counted again (cheap next to the copy), prefix sums give every range its
+// place in the outputs, and the ranges fill them in parallel.
 // Returns 0, -1 when the file cannot be read, -2 when it changed between the passes.
 extern "C" int mcg_fasta_load(const char *path, uint8_t *bases, int64_t *offsets, uint8_t *names,
-                                  int64_t *name_offsets, int64_t n_records, int64_t n_bases,
-                                  int64_t name_bytes) {
+                              int64_t *name_offsets, int64_t n_records, int64_t n_bases,
+                              int64_t name_bytes) {
     Mapped m;
     if (!m.open(path)) return -1;
-    FastaOut o;
-    o.cap_records = n_records;
-    o.cap_bases = n_bases;
-    o.cap_names = name_bytes;
-    o.bases = bases;
-    o.offsets = offsets;
-    o.names = names;
-    o.name_offsets = name_offsets;
-    if (n_records == 0) {
-        offsets[0] = 0;
-        name_offsets[0] = 0;
-        return 0;
+    const std::vector<size_t> cuts = fasta_ranges(m.data, m.size);
+    std::vector<FastaOut> counted;
+    fasta_count(m.data, cuts, &counted);
+    const size_t n = cuts.size() - 1;
+    std::vector<FastaOut> fill(n);
+    int64_t rec = 0, nb = 0, nn = 0;
+    for (size_t i = 0; i < n; ++i) {
+        fill[i].n_records = rec;
+        fill[i].n_bases = nb;
+        fill[i].name_bytes = nn;
+        rec += counted[i].n_records;
+        nb += counted[i].n_bases;
+        nn += counted[i].name_bytes;
+        fill[i].cap_records = rec;      // a range must stay inside its own slice
+        fill[i].cap_bases = nb;
+        fill[i].cap_names = nn;
+        fill[i].bases = bases;
+        fill[i].offsets = offsets;
+        fill[i].names = names;
+        fill[i].name_offsets = name_offsets;
     }
-    fasta_pass<true>(m.data, m.size, &o);
-    if (o.overflow || o.n_records != n_records || o.n_bases != n_bases || o.name_bytes != name_bytes)
-        return -2;
+    if (rec != n_records || nb != n_bases || nn != name_bytes) return -2;
+    offsets[0] = 0;
+    name_offsets[0] = 0;
+    if (n_records == 0) return 0;
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (size_t i; (i = next.fetch_add(1)) < n;)
+            fasta_pass<true>(m.data + cuts[i], cuts[i + 1] - cuts[i], &fill[i]);
+    };
+    const size_t workers = std::min<size_t>(n, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < workers; ++t) pool.emplace_back(work);
+    work();
+    for (std::thread &t : pool) t.join();
+    for (size_t i = 0; i < n; ++i)
+        if (fill[i].overflow || fill[i].n_records != fill[i].cap_records ||
+            fill[i].n_bases != fill[i].cap_bases || fill[i].name_bytes != fill[i].cap_names)
+            return -2;
+    offsets[n_records] = n_bases;
+    name_offsets[n_records] = name_bytes;
     return 0;
 }

@@ -27,8 +27,10 @@ def _check(got, want):
 
 
 @pytest.mark.parametrize("min_length", [1000, 60])
-def test_get_cov_len_matches_reference(ingest, min_length):
+def test_get_cov_len_matches_reference(ingest, min_length, monkeypatch):
     d, g = ingest
+    if min_length == 60:
+        monkeypatch.setenv("MCG_FASTA_RANGE_BYTES", "2000")     # ~30 parallel ranges
     got = feature_utils.get_cov_len(os.path.join(d, "contigs.fasta"), g["contig_names_rev"],
                                     min_length, os.path.join(d, "abundance.tsv"))
     _check(got, g["cases"]["plain_%d" % min_length])
@@ -60,8 +62,13 @@ def test_no_long_contig_exits(ingest):
                                   10 ** 7, os.path.join(d, "abundance.tsv"))
 
 
-def test_native_reader_matches_python_restatement(tmp_path):
-    """mcg_fasta_load against the pure-Python SimpleFastaParser restatement on hostile text."""
+@pytest.mark.parametrize("range_bytes", [None, "7", "64"])
+def test_native_reader_matches_python_restatement(tmp_path, monkeypatch, range_bytes):
+    """mcg_fasta_load against the pure-Python SimpleFastaParser restatement on hostile text;
+    with MCG_FASTA_RANGE_BYTES the file is cut into many record-aligned ranges that are
+    parsed in parallel (the default only does that above 8 MB)."""
+    if range_bytes:
+        monkeypatch.setenv("MCG_FASTA_RANGE_BYTES", range_bytes)
     rng = np.random.default_rng(3)
     pieces = [">", ">>", "> ", ">a b", "ACGT", "acgtn", " ", "  ", "\t", "\n", "\r\n", "\r",
               "\n\n", "NNNN", ">x\ty z", "A C G T", "GATTACA" * 30, "\x0b", ";c"]
