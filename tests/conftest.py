@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The tests bind the in-tree shared library; build it when the sources are newer (nvcc
+    cross-compiles sm_100a without a GPU).  The package itself never builds on import: a
+    missing library is an error there."""
+    from metacoag_b200 import build
+    return build.build_library()
