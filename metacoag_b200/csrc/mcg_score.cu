@@ -936,8 +936,11 @@ constexpr int kDeferBit = 1 << 30;
 // either MAX_WEIGHT or above 680 / ln 10 = 295.3, so it cannot be the argmin of a contig that
 // has a non-deferred weight below kGuardWeight.  Only contigs without such a weight go to the
 // redo list.
-template <bool GUARD>
-__global__ void __launch_bounds__(kProbThreads, GUARD ? 1 : 4)
+//
+// WARPS per CTA: 8, or 16 for sample counts whose terms leave room for one CTA per SM only
+// (S ~ 100): twice the warps next to the same shared bin terms.
+template <bool GUARD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (GUARD || WARPS > 8) ? 1 : 4)
 prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
             long long g0, int ncols, int ncols_pad, int pitch, ScoreOut out,
             int32_t *__restrict__ status, RedoList redo) {
@@ -946,12 +949,12 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
     double *LT = ET + 16;                             // 128
     double *AT = LT + 128;                            // [8 warps][2 rows][S][4]
     const int at_row = 4 * S;
-    double *BT = AT + kProbWarps * kProbRows * at_row;   // [ncols][pitch]
+    double *BT = AT + WARPS * kProbRows * at_row;   // [ncols][pitch]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 16) ET[tid] = g_exp_table[tid];
     if (tid < 128) LT[tid] = g_log_table[tid];
-    for (int idx = tid; idx < ncols * S; idx += kProbThreads) {
+    for (int idx = tid; idx < ncols * S; idx += WARPS * 32) {
         const int c = idx / S, q = idx - c * S;
         const long long row = B.index ? B.index[B.first + g0 + c] : (B.first + g0 + c);
         const long long off = row * S + q;
@@ -964,10 +967,10 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
     __syncthreads();
 
     double *at = AT + warp * kProbRows * at_row;
-    const long long n_warps = static_cast<long long>(gridDim.x) * kProbWarps;
+    const long long n_warps = static_cast<long long>(gridDim.x) * WARPS;
     const long long n_iter = (A.n + kProbRows - 1) / kProbRows;
     const bool last_group = g0 + ncols >= B.n;
-    for (long long it = static_cast<long long>(blockIdx.x) * kProbWarps + warp; it < n_iter;
+    for (long long it = static_cast<long long>(blockIdx.x) * WARPS + warp; it < n_iter;
          it += n_warps) {
         const long long r0 = it * kProbRows;
         __syncwarp();
@@ -1315,8 +1318,8 @@ __global__ void scatter_redo_kernel(const int *__restrict__ count, const long lo
     out_w[pos[i]] = w[i];
 }
 
-static size_t prob_smem_bytes(int S, long long group) {
-    return sizeof(double) * (16 + 128 + kProbWarps * kProbRows * 4 * S + bin_pitch(S) * group);
+static size_t prob_smem_bytes(int S, long long group, int warps = kProbWarps) {
+    return sizeof(double) * (16 + 128 + warps * kProbRows * 4 * S + bin_pitch(S) * group);
 }
 
 // Can the two-kernel rule-C path take S samples at all (one warp of bins per group)?
@@ -1343,15 +1346,24 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
     if (group < 32) group = 32;
     const long long n_groups = (b.n + group - 1) / group;
     group = ((b.n + n_groups - 1) / n_groups + 31) / 32 * 32;
-    const size_t prob_smem = prob_smem_bytes(S, group);
+    // When even the smallest group leaves room for one 8-warp CTA per SM only (S ~ 100), a
+    // 16-warp CTA shares the same bin terms between twice the warps, if it fits.
+    int warps = kProbWarps;
+    if (guard && 2 * prob_smem_bytes(S, group) > 220 * 1024 &&
+        prob_smem_bytes(S, group, 16) <= 200 * 1024)
+        warps = 16;
+    const size_t prob_smem = prob_smem_bytes(S, group, warps);
     if (!(ctx->device < 64 && attr[ctx->device])) {
         MCG_CUDA(ctx, cudaFuncSetAttribute(dist2_kernel<0>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(kDistSmem)));
-        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<false>,
+        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<false, 8>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            96 * 1024));
-        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<true>,
+        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<true, 8>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+        MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<true, 16>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            200 * 1024));
         if (ctx->device < 64) attr[ctx->device] = true;
@@ -1397,7 +1409,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc);
         mcg_timer_end(ctx, T_DIST);
         MCG_KERNEL_CHECK(ctx);
-        long long blocks = (ac.n + kProbWarps * kProbRows - 1) / (kProbWarps * kProbRows);
+        long long blocks = (ac.n + warps * kProbRows - 1) / (warps * kProbRows);
         const long long cap = 4LL * ctx->sm_count * 4;
         if (blocks > cap) blocks = cap;
         mcg_timer_begin(ctx, T_PROB);
@@ -1405,14 +1417,17 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
             const int ncols = static_cast<int>(b.n - g0 < group ? b.n - g0 : group);
             const int ncols_pad = (ncols + 31) / 32 * 32;
             const size_t smem_g = prob_smem - sizeof(double) * pitch * (group - ncols);
-            if (guard)
-                prob_kernel<true><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
-                                    ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch,
-                                                   shifted, d_status, redo);
+            if (guard && warps == 16)
+                prob_kernel<true, 16><<<static_cast<unsigned>(blocks), 512, smem_g, ctx->stream>>>(
+                    ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch, shifted, d_status, redo);
+            else if (guard)
+                prob_kernel<true, 8><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
+                                       ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad,
+                                                      pitch, shifted, d_status, redo);
             else
-                prob_kernel<false><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
-                                     ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch,
-                                                    shifted, d_status, redo);
+                prob_kernel<false, 8><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
+                                        ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad,
+                                                       pitch, shifted, d_status, redo);
             MCG_KERNEL_CHECK(ctx);
         }
         // (the timer holds one interval: with S > 30 it closes after the redo pass below)
