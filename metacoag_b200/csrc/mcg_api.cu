@@ -1281,9 +1281,10 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
                     ScoreOut out;
                     out.argmin = ctx->argmin.as<int32_t>() + c0;
                     out.wmin = ctx->wmin.as<double>() + c0;
-                    // the same kernels whatever the size of the range: the weights must not
+                    // the kernels the whole set would take in one call (two-kernel path from
+                    // 2048 contigs), whatever the size of the range: the weights must not
                     // depend on where the upload happened to cut the waves
-                    ctx->force_split = true;
+                    ctx->force_split = n >= 2048;
                     rc = mcg_k_pairs(ctx, a, centroid_side(ctx), ctx->n_samples, out,
                                      ctx->status.as<int32_t>());
                     ctx->force_split = false;

@@ -121,11 +121,21 @@ def test_config3_shard_full_size():
         ctx.close()
 
 
-def test_config4_flye_lengths():
+def test_config4_flye_lengths(monkeypatch):
     ctx = _lib.Context(0)
     try:
         tabs, blob = build(ctx, "flye", 2000, 10, 200, 1004)
         assert np.diff(tabs["offsets"]).max() > 3_000_000
-        check_scoring(ctx, tabs, blob, 12, 3)
+        arg, w = check_scoring(ctx, tabs, blob, 12, 3)
+        # fewer than 2048 contigs but > 64 MB of bases: the plug-in call runs in waves and must
+        # still take the kernels (and give the bits) of the staged call, for any thread count
+        # and wave size
+        cen_prof, cen_cov = ctx.bin_profiles(tabs["members"], tabs["seg"])
+        rng = np.random.default_rng(4)
+        for _ in range(10):
+            ctx.set_host_pack_threads(int(rng.choice([0, 1, 3, 7, 15, 24])))
+            monkeypatch.setenv("MCG_WAVE_DIV", str(int(rng.choice([2, 5, 12, 30]))))
+            arg3, w3 = ctx.featurise_score(blob, tabs["offsets"], tabs["coverage"], cen_prof, cen_cov)
+            assert np.array_equal(arg3, arg) and np.array_equal(w3, w)
     finally:
         ctx.close()
