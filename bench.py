@@ -285,14 +285,42 @@ def main():
     d_wmin = torch.empty(n, dtype=torch.float64, device=dev)
     fp64_peak = ctx.fp64_peak()
 
+    # N > 1: the two collectives of a step run on their own stream.  The centroid broadcast of
+    # step k overlaps its scan (the scorer waits for it), the all-gather of step k overlaps the
+    # scan of step k + 1; the scorer of step k + 1 waits for that gather before it overwrites
+    # the assignment buffers, and the next broadcast waits for the scorer that reads the
+    # centroids.  Every step still does all of its work; only the kernels stay on the critical
+    # path.
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_bcast = torch.cuda.Event()
+    ev_scored = torch.cuda.Event()
+    ev_gathered = torch.cuda.Event()
+    gathered = [None]
+
     def step():
-        if world > 1:
+        if world == 1:
+            ctx.step_resident(d_argmin.data_ptr(), d_wmin.data_ptr())
+            return d_argmin, d_wmin
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_scored)          # the previous scorer still reads the centroids
             parallel.broadcast_centroids(d_cen_prof, d_cen_cov, src=0)
-            ctx.set_centroids_dev(d_cen_prof.data_ptr(), d_cen_cov.data_ptr(), N_BINS)
-        ctx.step_resident(d_argmin.data_ptr(), d_wmin.data_ptr())
-        if world > 1:
-            return parallel.gather_assignments(d_argmin, d_wmin, counts=[n] * world)
-        return d_argmin, d_wmin
+            ev_bcast.record(comm)
+        ctx.step_featurise()
+        stream.wait_event(ev_bcast)
+        stream.wait_event(ev_gathered)          # the previous gather still reads the buffers
+        ctx.set_centroids_dev(d_cen_prof.data_ptr(), d_cen_cov.data_ptr(), N_BINS)
+        ctx.step_score(d_argmin.data_ptr(), d_wmin.data_ptr())
+        ev_scored.record(stream)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_scored)
+            gathered[0] = parallel.gather_assignments(d_argmin, d_wmin, counts=[n] * world)
+            ev_gathered.record(comm)
+        return gathered[0]
+
+    def drain():
+        """The timed region ends when the last gather has landed."""
+        if comm is not None:
+            stream.wait_stream(comm)
 
     for _ in range(args.warmup):
         step()
@@ -321,6 +349,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    drain()
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)

@@ -216,6 +216,12 @@ int mcg_set_centroids(mcg_ctx *ctx, const double *cen_prof, const double *cen_co
 int mcg_set_centroids_dev(mcg_ctx *ctx, const void *d_cen_prof, const void *d_cen_cov,
                           int64_t n_bins);
 int mcg_step_resident(mcg_ctx *ctx, void *d_argmin, void *d_wmin);
+/* The two halves of mcg_step_resident -- scan + normalise + coverage terms, then rule C against
+ * the resident centroids -- for callers that put something between them, e.g. an NCCL
+ * broadcast of the centroids that runs on another stream while the scan is in flight
+ * (mcg_set_centroids_dev after it, before mcg_step_score). */
+int mcg_step_featurise(mcg_ctx *ctx);
+int mcg_step_score(mcg_ctx *ctx, void *d_argmin, void *d_wmin);
 int mcg_get_assignments(mcg_ctx *ctx, int32_t *argmin, double *wmin);
 
 /* Per-kernel device times of the last mcg_step_resident / mcg_featurise_score,

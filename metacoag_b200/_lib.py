@@ -62,6 +62,8 @@ SIGNATURES = {
     "mcg_set_centroids": (_int, [_vp, _vp, _vp, _i64]),
     "mcg_set_centroids_dev": (_int, [_vp, _vp, _vp, _i64]),
     "mcg_step_resident": (_int, [_vp, _vp, _vp]),
+    "mcg_step_featurise": (_int, [_vp]),
+    "mcg_step_score": (_int, [_vp, _vp, _vp]),
     "mcg_get_assignments": (_int, [_vp, _vp, _vp]),
     "mcg_profile": (_int, [_vp, _int]),
     "mcg_timings": (_int, [_vp, _vp, _vp]),
@@ -451,6 +453,12 @@ class Context:
 
     def step_resident(self, d_argmin=None, d_wmin=None):
         self._check(self.lib.mcg_step_resident(self.handle, d_argmin, d_wmin))
+
+    def step_featurise(self):
+        self._check(self.lib.mcg_step_featurise(self.handle))
+
+    def step_score(self, d_argmin=None, d_wmin=None):
+        self._check(self.lib.mcg_step_score(self.handle, d_argmin, d_wmin))
 
     def get_assignments(self):
         argmin = np.zeros(self.n_contigs, dtype=np.int32)

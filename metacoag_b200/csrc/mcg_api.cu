@@ -1219,6 +1219,36 @@ static int step_locked(mcg_ctx *ctx, int32_t *d_argmin, double *d_wmin) {
     return score_centroids_locked(ctx, nullptr, n, nullptr, d_argmin, d_wmin);
 }
 
+// The two halves of mcg_step_resident, for callers that put something between them (the
+// multi-GPU bench receives the broadcast centroids while the scan is running).
+extern "C" int mcg_step_featurise(mcg_ctx *ctx) {
+    MCG_ENTER(ctx);
+    if (ctx->n_contigs == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no contigs resident");
+    if (ctx->n_cov != ctx->n_contigs)
+        return mcg_fail(ctx, MCG_ERR_STATE, "coverage rows (%lld) != contigs (%lld)",
+                        (long long)ctx->n_cov, (long long)ctx->n_contigs);
+    MCG_TRY(scan_locked(ctx));
+    return cov_terms_locked(ctx);
+}
+
+extern "C" int mcg_step_score(mcg_ctx *ctx, void *d_argmin, void *d_wmin) {
+    MCG_ENTER(ctx);
+    MCG_TRY(need_features(ctx));
+    if (ctx->n_bins == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no centroids resident");
+    const int64_t n = ctx->n_contigs;
+    int32_t *a = static_cast<int32_t *>(d_argmin);
+    double *w = static_cast<double *>(d_wmin);
+    if (!a) {
+        MCG_TRY(mcg_reserve(ctx, ctx->argmin, sizeof(int32_t) * n));
+        a = ctx->argmin.as<int32_t>();
+    }
+    if (!w) {
+        MCG_TRY(mcg_reserve(ctx, ctx->wmin, sizeof(double) * n));
+        w = ctx->wmin.as<double>();
+    }
+    return score_centroids_locked(ctx, nullptr, n, nullptr, a, w);
+}
+
 extern "C" int mcg_step_resident(mcg_ctx *ctx, void *d_argmin, void *d_wmin) {
     MCG_ENTER(ctx);
     return step_locked(ctx, static_cast<int32_t *>(d_argmin), static_cast<double *>(d_wmin));
