@@ -111,6 +111,18 @@ int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, int64_t n, 
 int mcg_fasta_index(const char *path, int64_t *n_records, int64_t *n_bases, int64_t *name_bytes);
 int mcg_fasta_load(const char *path, uint8_t *bases, int64_t *offsets, uint8_t *names,
                    int64_t *name_offsets, int64_t n_records, int64_t n_bases, int64_t name_bytes);
+/* metacoag:1210-1251 (the per-bin FASTA writer, inline in the CLI): the reference parses the
+ * contigs file again and writes ">{record.id}\n{str(record.seq)}\n" for every binned record,
+ * in file order, to {prefix}bins/{prefix}bin_{name}.fasta or
+ * {prefix}low_quality_bins/{prefix}bin_{name}_seqs.fasta.  Here the records come from the
+ * blob mcg_fasta_load filled: file_of_record[i] is the index into paths of record i's output
+ * (-1 = the record is in no bin).  Outputs are truncated ("w+") and written in parallel, one
+ * worker per file; an output without records is created empty.  Host-only.
+ * Returns 0, -(1 + i) when paths[i] could not be written, -1000000000 for a bad file index. */
+int mcg_write_bin_fastas(const uint8_t *bases, const int64_t *offsets, const uint8_t *names,
+                         const int64_t *name_offsets, int64_t n_records,
+                         const int32_t *file_of_record, const char *const *paths,
+                         int32_t n_files);
 /* Last ASCII load: stats[0] bytes copied host->device for the bases, [1] bases packed by
  * host threads, [2] bases packed by the kernel, [3] host threads used. */
 int mcg_ingest_stats(mcg_ctx *ctx, int64_t stats[4]);

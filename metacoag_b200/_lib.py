@@ -75,6 +75,7 @@ SIGNATURES = {
     "mcg_pack_2bit_host": (_int, [_vp, _vp, _i64, _vp, _int]),
     "mcg_fasta_index": (_int, [_c.c_char_p, _vp, _vp, _vp]),
     "mcg_fasta_load": (_int, [_c.c_char_p, _vp, _vp, _vp, _vp, _i64, _i64, _i64]),
+    "mcg_write_bin_fastas": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _c.c_int32]),
 }
 
 
@@ -157,6 +158,35 @@ def read_fasta(path, pinned=False):
     text = names.tobytes().decode("latin-1")
     no = name_offsets.tolist()
     return [text[no[i]:no[i + 1]] for i in range(n)], bases, offsets
+
+
+def write_bin_fastas(names, bases, offsets, file_of_record, paths):
+    """Records of the contig blob -> one FASTA file per entry of ``paths``
+    (``>{name}\\n{sequence}\\n`` in record order, metacoag:1236-1251); ``file_of_record[i]`` is
+    the index of record i's file or -1.  Host-only."""
+    lib = load_library()
+    n = len(names)
+    encoded = [s.encode("latin-1") for s in names]
+    name_offsets = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum([len(b) for b in encoded], out=name_offsets[1:])
+    name_blob = np.frombuffer(b"".join(encoded), dtype=np.uint8) if name_offsets[-1] else np.zeros(1, np.uint8)
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    if bases.shape[0] == 0:
+        bases = np.zeros(1, np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    file_of_record = np.ascontiguousarray(file_of_record, dtype=np.int32)
+    if offsets.shape[0] != n + 1 or file_of_record.shape[0] != n:
+        raise ValueError("names, offsets and file_of_record disagree about the record count")
+    raw = [os.fsencode(p) for p in paths]
+    c_paths = (_c.c_char_p * max(1, len(raw)))(*raw)
+    rc = lib.mcg_write_bin_fastas(_ptr(bases), _ptr(offsets), _ptr(name_blob), _ptr(name_offsets),
+                                  n, _ptr(file_of_record), _c.cast(c_paths, _c.c_void_p),
+                                  len(raw))
+    if rc == -1000000000:
+        raise ValueError("file_of_record holds an index outside paths")
+    if rc != 0:
+        raise OSError("could not write %s" % paths[-rc - 1])
 
 
 class Context:

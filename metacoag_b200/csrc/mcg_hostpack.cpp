@@ -163,6 +163,7 @@ extern "C" int mcg_hostpack_level(void) {
 //   (pinned) buffers.
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <cstdlib>
 #include <thread>
 #include <vector>
@@ -383,4 +384,81 @@ extern "C" int mcg_fasta_load(const char *path, uint8_t *bases, int64_t *offsets
     offsets[n_records] = n_bases;
     name_offsets[n_records] = name_bytes;
     return 0;
+}
+
+// Per-bin FASTA output (metacoag:1210-1251): the reference parses the contigs file a second
+// time and writes ">{record.id}\n{record.seq}\n" for every binned record, in file order, to
+// the file of its bin.  The staged blob already holds record.id and str(record.seq) of every
+// record in file order (mcg_fasta_load), so the second parse is not needed: file_of_record[i]
+// picks the output of record i (-1 = in no bin), every output is sized, gathered and written
+// by one worker (outputs are independent, so they go in parallel).  Files are truncated like
+// the reference's open(..., "w+"); an output without records is created empty.
+// Returns 0, or -(1 + index) of the first output that could not be written; -1000000000 for a
+// file index out of range.
+extern "C" int mcg_write_bin_fastas(const uint8_t *bases, const int64_t *offsets,
+                                    const uint8_t *names, const int64_t *name_offsets,
+                                    int64_t n_records, const int32_t *file_of_record,
+                                    const char *const *paths, int32_t n_files) {
+    if (n_files <= 0) return 0;
+    std::vector<std::vector<int64_t>> members(static_cast<size_t>(n_files));
+    for (int64_t i = 0; i < n_records; ++i) {
+        const int32_t f = file_of_record[i];
+        if (f < 0) continue;
+        if (f >= n_files) return -1000000000;
+        members[static_cast<size_t>(f)].push_back(i);
+    }
+    std::atomic<int32_t> next(0);
+    std::atomic<int32_t> failed(n_files);
+    auto work = [&]() {
+        std::vector<uint8_t> buf;
+        for (int32_t f; (f = next.fetch_add(1)) < n_files;) {
+            const std::vector<int64_t> &recs = members[static_cast<size_t>(f)];
+            size_t bytes = 0;
+            for (int64_t i : recs)
+                bytes += static_cast<size_t>(name_offsets[i + 1] - name_offsets[i]) +
+                         static_cast<size_t>(offsets[i + 1] - offsets[i]) + 3;
+            buf.resize(bytes);
+            uint8_t *p = buf.data();
+            for (int64_t i : recs) {
+                const size_t nn = static_cast<size_t>(name_offsets[i + 1] - name_offsets[i]);
+                const size_t nb = static_cast<size_t>(offsets[i + 1] - offsets[i]);
+                *p++ = '>';
+                if (nn) memcpy(p, names + name_offsets[i], nn);
+                p += nn;
+                *p++ = '\n';
+                if (nb) memcpy(p, bases + offsets[i], nb);
+                p += nb;
+                *p++ = '\n';
+            }
+            bool ok = false;
+            const int fd = ::open(paths[f], O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            if (fd >= 0) {
+                ok = true;
+                size_t done = 0;
+                while (done < bytes) {
+                    const ssize_t w = ::write(fd, buf.data() + done, bytes - done);
+                    if (w < 0) {
+                        if (errno == EINTR) continue;
+                        ok = false;
+                        break;
+                    }
+                    done += static_cast<size_t>(w);
+                }
+                if (::close(fd) != 0) ok = false;
+            }
+            if (!ok) {
+                int32_t cur = failed.load();
+                while (f < cur && !failed.compare_exchange_weak(cur, f)) {
+                }
+            }
+        }
+    };
+    const size_t workers = std::min<size_t>(static_cast<size_t>(n_files),
+                                            std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < workers; ++t) pool.emplace_back(work);
+    work();
+    for (std::thread &t : pool) t.join();
+    const int32_t bad = failed.load();
+    return bad < n_files ? -(1 + bad) : 0;
 }

@@ -168,6 +168,29 @@ def main():
         assert np.array_equal(blob, b2) and np.array_equal(offsets, o2)
         out["fasta_reader"] = {"file_mb": size / 1e6, "native_s": nat, "native_gb_s": size / nat / 1e9,
                                "python_parse_and_join_s": py, "speedup": py / nat}
+
+        # ---- per-bin FASTA writer (metacoag:1231-1257) ------------------------------------------------
+        n_files = 200
+        dest = (np.arange(len(names)) * 7919 % (n_files + 20)).astype(np.int32)
+        dest[dest >= n_files] = -1
+        paths = [os.path.join(tmp, "bin_%d.fasta" % i) for i in range(n_files)]
+        t0 = time.perf_counter()
+        _lib.write_bin_fastas(names, blob, offsets, dest, paths)
+        nat = time.perf_counter() - t0
+        written = sum(os.path.getsize(p) for p in paths)
+        t0 = time.perf_counter()                         # the reference's way: second parse + write()
+        files = [open(os.path.join(tmp, "ref_%d.fasta" % i), "w+") for i in range(n_files)]
+        for k, (name, seq) in enumerate(feature_utils._fasta_records(path)):
+            if dest[k] >= 0:
+                files[dest[k]].write(f">{name}\n{seq}\n")
+        for fh in files:
+            fh.close()
+        py = time.perf_counter() - t0
+        for i in range(0, n_files, 17):
+            assert open(paths[i], "rb").read() == open(os.path.join(tmp, "ref_%d.fasta" % i), "rb").read()
+        out["bin_fasta_writer"] = {"files": n_files, "mb_written": written / 1e6, "native_s": nat,
+                                   "native_gb_s": written / nat / 1e9,
+                                   "python_second_parse_and_write_s": py, "speedup": py / nat}
     print(json.dumps(out, indent=1))
 
 
