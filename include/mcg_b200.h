@@ -93,6 +93,20 @@ int mcg_scan(mcg_ctx *ctx);
  * environment, else the hardware threads minus one (the caller feeds the copy engine).  (Replaces the per-sequence pickling
  * to a worker pool of feature_utils.py:97-104.) */
 int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads);
+/* Rule C at scale (mcg_score_centroids / mcg_step_* / mcg_featurise_score without the weight
+ * matrix) is a branch and bound.  log prob_cov <= 0 and is at most a number U of the contig
+ * alone (matching_utils.py:42-66: a Poisson term is largest when the two coverages agree), and
+ * -log prob_comp grows with the tetramer distance (matching_utils.py:36-39).  So once a contig
+ * has the weight W of one bin (its nearest centroid), bins beyond the distance where
+ * -log10 prob_comp passes W + U / ln 10 have a weight strictly above W: they are listed out, the
+ * few that remain are scored exactly as before, and argmin / minimum weight
+ * (label_prop_utils.py:340-345, first minimum) are the same bits with and without.  On by
+ * default; 0 scores every pair (measurement, tests). */
+int mcg_set_prune(mcg_ctx *ctx, int enabled);
+/* The last pruned rule-C chunk (synchronises the stream): [0] pairs listed as candidates,
+ * [1] capacity of the list, [2] all pairs of the chunk, [3] 1 when the list was used, 0 when it
+ * overflowed and every pair was scored (or pruning is off). */
+int mcg_prune_stats(mcg_ctx *ctx, int64_t stats[4]);
 /* The host-side packer on its own: ASCII contigs -> the MCG_ENC_2BIT layout described above
  * (packed has 16 * sum_c ceil(len_c / 64) bytes).  Pure host code, no device needed.
  * level -1 = best SIMD variant of this CPU, 0 scalar, 1 AVX2, 2 AVX-512BW, 3 AVX2 with a

@@ -71,6 +71,8 @@ SIGNATURES = {
     "mcg_fp64_peak": (_int, [_vp, _vp]),
     "mcg_last_redo_count": (_int, [_vp, _vp]),
     "mcg_set_host_pack_threads": (_int, [_vp, _int]),
+    "mcg_set_prune": (_int, [_vp, _int]),
+    "mcg_prune_stats": (_int, [_vp, _vp]),
     "mcg_ingest_stats": (_int, [_vp, _vp]),
     "mcg_pack_2bit_host": (_int, [_vp, _vp, _i64, _vp, _int]),
     "mcg_fasta_index": (_int, [_c.c_char_p, _vp, _vp, _vp]),
@@ -240,6 +242,16 @@ class Context:
         out = dict(zip(TIMER_NAMES, (float(x) for x in ms)))
         out["launches"] = int(launches.value)
         return out
+
+    def set_prune(self, enabled):
+        """Rule-C branch and bound on / off (include/mcg_b200.h); results do not change."""
+        self._check(self.lib.mcg_set_prune(self.handle, int(bool(enabled))))
+
+    def prune_stats(self):
+        """The candidate list of the last pruned rule-C chunk (include/mcg_b200.h)."""
+        st = (_c.c_int64 * 4)()
+        self._check(self.lib.mcg_prune_stats(self.handle, st))
+        return {"candidates": st[0], "capacity": st[1], "pairs": st[2], "used": bool(st[3])}
 
     def set_host_pack_threads(self, threads):
         """Host threads that pack ASCII chunks during a load (0 = copy engine only)."""

@@ -1407,6 +1407,18 @@ extern "C" int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads) {
     return MCG_OK;
 }
 
+extern "C" int mcg_set_prune(mcg_ctx *ctx, int enabled) {
+    MCG_ENTER(ctx);
+    ctx->prune = enabled ? 1 : 0;
+    return MCG_OK;
+}
+
+extern "C" int mcg_prune_stats(mcg_ctx *ctx, int64_t stats[4]) {
+    MCG_ENTER(ctx);
+    if (!stats) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    return mcg_k_prune_stats(ctx, stats);
+}
+
 extern "C" int mcg_ingest_stats(mcg_ctx *ctx, int64_t stats[4]) {
     MCG_ENTER(ctx);
     if (!stats) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");

@@ -42,6 +42,7 @@ struct mcg_ctx {
     cudaEvent_t copy2_done = nullptr;
     void *pinned_pack = nullptr;          // host-packed contigs, staged for the copy engine
     size_t pinned_pack_cap = 0;
+    int prune = 1;                        // rule-C branch and bound (mcg_set_prune)
     int host_pack_threads = -1;           // -1: MCG_HOST_PACK_THREADS or the hardware threads - 1
     int64_t ingest_stats[4] = {};         // last ASCII load: h2d bytes, host-packed bases,
                                           // GPU-packed bases, host threads
@@ -83,6 +84,8 @@ struct mcg_ctx {
     DevBuf status;             // int32 [4] device-side flags (0: domain error)
     DevBuf scratch[6];
     bool force_split = false;  // rule C always on the two-kernel path (waves: results must not depend on batch size)
+    bool cand_valid = false;   // scratch[3] starts with the candidate count of the last pruned rule-C chunk
+    long long cand_cap = 0, cand_pairs = 0;
     bool redo_valid = false;   // scratch[4] starts with the redo count of the last guarded rule-C call
     void *pinned = nullptr;    // small pinned staging block
     size_t pinned_cap = 0;
@@ -193,6 +196,7 @@ int mcg_k_comp_prob(mcg_ctx *ctx, const double *d_dist, double *d_out, int64_t n
 int mcg_k_cov_prob(mcg_ctx *ctx, const double *d_c1, const double *d_c2, int64_t n, int S,
                    double *d_out);
 int mcg_k_fp64_peak(mcg_ctx *ctx, double *tflops);
+int mcg_k_prune_stats(mcg_ctx *ctx, int64_t stats[4]);
 
 // mcg_frontier.cu
 int mcg_k_bfs(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices, int64_t n_vertices,

@@ -122,6 +122,8 @@ struct MathConst {
     double log_inv_denom_intra;                       // -log(sd_intra * sqrt(2 pi))
     double sd_ratio;                                  // sd_intra / sd_inter
     double log_sd_ratio;
+    // log rho = qa d^2 + qb d + qc (bound_kernel): 4 qa, qb, qc, 1 / (2 qa)
+    double prune_4a, prune_b, prune_c, prune_inv_2a;
 };
 __constant__ MathConst c_math;
 
@@ -925,6 +927,12 @@ struct RedoList {
     long long *rows;      // table row of the contig
     long long *pos;       // where its result goes (index into ScoreOut::argmin / wmin)
 };
+// Gate between the two ways to finish rule C: the candidate kernels run when the list
+// bound_kernel wrote holds every candidate (total <= cap), prob_kernel over all pairs otherwise.
+struct CandGate {
+    const int *total;   // nullptr: no candidate list, prob_kernel always runs
+    int cap;
+};
 constexpr double kGuardLog = -680.0;      // log prob_cov below this: the pair is deferred
 constexpr double kGuardWeight = 295.0;    // 295 ln 10 = 679.3 < 680: no deferred pair can beat it
 constexpr int kDeferBit = 1 << 30;
@@ -943,7 +951,9 @@ template <bool GUARD, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (GUARD || WARPS > 8) ? 1 : 4)
 prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
             long long g0, int ncols, int ncols_pad, int pitch, ScoreOut out,
-            int32_t *__restrict__ status, RedoList redo) {
+            int32_t *__restrict__ status, RedoList redo, CandGate gate) {
+    // with a candidate list (bound_kernel) this kernel only runs when the list overflowed
+    if (gate.total && *gate.total <= gate.cap) return;
     extern __shared__ __align__(16) double sm[];
     double *ET = sm;                                  // 16
     double *LT = ET + 16;                             // 128
@@ -1108,6 +1118,297 @@ prob_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long
                 }
             }
         }
+    }
+}
+
+
+// ---- rule C as a branch and bound --------------------------------------------------------------
+// The argmin of rule C (label_prop_utils.py:340-345) needs very few of the B weights of a contig.
+// Two facts about w = -(log prob_comp + log prob_cov) / ln 10:
+//   * -log prob_comp = log(1 + rho) >= log rho = qa d^2 + qb d + qc with rho = (sd_i / sd_e)
+//     exp(ae - ai): a parabola that grows with the tetramer distance d (for d > ~0.05 the two are
+//     the same double, see log_comp_prob_warp; where the intra Gaussian leaves the normal range
+//     the weight is above 300 or MAX_WEIGHT);
+//   * log prob_cov = min(A, B) <= A = sum_s max(x_s, L), and x_s = c1 log c2 - lgamma(c1 + 1) - c2 is
+//     largest at c2 = c1: whatever the bin, A <= U = sum_s max(c1 log c1 - lgamma(c1 + 1) - c1, L),
+//     a number of the contig alone.
+// So with W the weight of ANY bin of the contig (here: its nearest centroid), every bin with
+// parabola(d) > W ln 10 + U has a weight strictly above W and is neither the argmin nor a
+// first-index tie.  bound_kernel (one warp per contig) scores the nearest centroid, turns W into
+// a d^2 threshold and lists the bins under it, in bin order, as the contig's candidates (~1 of
+// 200 on the config-2 set); cand_score_kernel scores the listed pairs with exactly the
+// arithmetic of prob_kernel (one thread per pair) and cand_argmin_kernel takes the first
+// minimum per contig, with the same None / deferral rules.  A contig without a usable W
+// (nothing within d < 0.17, or W >= kPruneMaxWeight) lists every bin.  Margins of 1e-9 relative on W, U
+// and d are far above the rounding of either side.  When the list would exceed its capacity
+// (a quarter of all pairs) the candidate kernels leave and prob_kernel scores every pair.
+constexpr double kPruneMaxWeight = 287.0;
+struct CandList {
+    int *total;          // [1] candidates of all contigs (keeps counting beyond cap)
+    int cap;
+    int *start, *count;  // [A.n] range of a contig
+    int2 *pair;          // [cap] (row of the chunk, bin)
+    double *w;           // [cap] weight; NaN = deferred (GUARD)
+};
+
+constexpr int kHeadSamples = 8;    // samples of the second, coverage-aware test of bound_kernel
+constexpr int kMaxSlabs = 64;      // 32-bin slabs per contig the candidate path takes (B <= 2048)
+
+// (c, log c) of the first kHeadSamples samples of every bin, sample-major, so that the 32 lanes
+// of bound_kernel (32 consecutive bins) read them coalesced: head[(2 q + {0,1}) * ldh + bin].
+__global__ void bin_head_kernel(ScoreSide B, int S, int nq, long long ldh,
+                                double *__restrict__ head) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= B.n * nq) return;
+    const long long j = i / nq;
+    const int q = static_cast<int>(i - j * nq);
+    const long long brow = B.index ? B.index[B.first + j] : (B.first + j);
+    head[(2 * q) * ldh + j] = B.cov[brow * S + q];
+    head[(2 * q + 1) * ldh + j] = B.logc[brow * S + q];
+}
+
+__global__ void __launch_bounds__(256)
+bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
+             const double *__restrict__ head, long long ldh, CandList cl,
+             int32_t *__restrict__ status) {
+    __shared__ double ET[16];
+    __shared__ double LT[128];
+    __shared__ double HA[8][2 * kHeadSamples];   // per warp: (c, m) of the contig's first samples
+    __shared__ unsigned MASK[8][kMaxSlabs];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < 16) ET[tid] = g_exp_table[tid];
+    if (tid < 128) LT[tid] = g_log_table[tid];
+    __syncthreads();
+    const int nq = S < kHeadSamples ? S : kHeadSamples;
+    const double sl = static_cast<double>(S) * c_math.log_floor;
+    const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wid; r < A.n;
+         r += n_warps) {
+        const double *row = d2 + r * ldc;
+        // nearest centroid (first index on ties)
+        double dm = INFINITY;
+        int jm = 0;
+        for (int j = lane; j < B.n; j += 32) {
+            const double v = row[j];
+            if (v < dm) { dm = v; jm = j; }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, dm, m);
+            const int oj = __shfl_xor_sync(0xffffffffu, jm, m);
+            if (od < dm || (od == dm && oj < jm)) { dm = od; jm = oj; }
+        }
+        // the contig's side: U (and its tail beyond the head samples), head terms for the
+        // coverage-aware test
+        const long long arow = A.index ? A.index[A.first + r] : (A.first + r);
+        double u = 0.0, u_tail = 0.0;   // lanes over samples
+        __syncwarp();
+        for (int q = lane; q < S; q += 32) {
+            const double ac = A.cov[arow * S + q], al = A.logc[arow * S + q];
+            const double am = -(A.lgam[arow * S + q] + c_math.log_floor);
+            double e = fma(ac, al, am) - ac;   // the most this sample can add
+            e = e > 0.0 ? e : 0.0;
+            u += e;
+            if (q >= nq) u_tail += e;
+            if (q < nq) { HA[wid][2 * q] = ac; HA[wid][2 * q + 1] = am; }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            u += __shfl_xor_sync(0xffffffffu, u, m);
+            u_tail += __shfl_xor_sync(0xffffffffu, u_tail, m);
+        }
+        __syncwarp();
+        double cov_upper = fma(u, 1.0 + 1e-9, sl);   // U, rounded up
+        if (cov_upper > 0.0) cov_upper = 0.0;
+        // weight of one bin, by the whole warp (NaN: prob_comp is 0 or not a plain number)
+        auto probe = [&](int j, double dd) -> double {
+            if (!(dd < 0.03)) return INFINITY;   // d < 0.17: prob_comp normal with room to spare
+            const long long brow = B.index ? B.index[B.first + j] : (B.first + j);
+            double s1 = 0.0, s2 = 0.0;
+            for (int q = lane; q < S; q += 32) {
+                const double ac = A.cov[arow * S + q], al = A.logc[arow * S + q];
+                const double am = -(A.lgam[arow * S + q] + c_math.log_floor);
+                const double bc = B.cov[brow * S + q], bl = B.logc[brow * S + q];
+                const double bm = -(B.lgam[brow * S + q] + c_math.log_floor);
+                add_poisson_excess(s1, ac, am, bc, bl);
+                add_poisson_excess(s2, bc, bm, ac, al);
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+            }
+            const double lpc = log_comp_prob_warp(dd, ET, LT, status);
+            return -(lpc + sl + (s1 < s2 ? s1 : s2)) * c_math.inv_ln10;
+        };
+        double w = probe(jm, dm);
+        // parabola(d) > W ln 10 + U  <=>  d > (-qb + sqrt(qb^2 + 4 qa target)) / (2 qa)
+        auto threshold = [&](double wv) -> double {
+            const double target = wv * (1.0 + 1e-9) * c_gauss.ln10 + cov_upper - c_math.prune_c;
+            double disc = fma(c_math.prune_4a, target, c_math.prune_b * c_math.prune_b);
+            if (!(disc > 0.0)) disc = 0.0;
+            double d = (sqrt(disc) - c_math.prune_b) * c_math.prune_inv_2a;
+            d = d > 0.0 ? d * (1.0 + 1e-9) : 0.0;
+            return d * d * (1.0 + 1e-15);
+        };
+        const int n_slabs = static_cast<int>((B.n + 31) >> 5);
+        double thr2 = (w < kPruneMaxWeight) ? threshold(w) : INFINITY;
+        if (!(thr2 < 0.045 * 0.045) && nq > 0) {
+            // The nearest centroid gave no bound, or a loose one (short contigs sit as close to
+            // a neighbour's centroid as to their own).  Second probe: the bin with the smallest
+            // LOWER bound of its weight from the distance and the head samples.
+            double lb = INFINITY;
+            int jb = 0;
+            for (int sb = 0; sb < n_slabs; ++sb) {
+                const int j = 32 * sb + lane;
+                if (j < B.n) {
+                    const double dd = row[j];
+                    double e1 = 0.0;
+                    const double *hp = head + j;
+                    for (int q = 0; q < nq; ++q)
+                        add_poisson_excess(e1, HA[wid][2 * q], HA[wid][2 * q + 1],
+                                           hp[(2 * q) * ldh], hp[(2 * q + 1) * ldh]);
+                    const double v = fma(c_math.prune_4a * 0.25, dd, -e1);
+                    if (v < lb) { lb = v; jb = j; }
+                }
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const double ol = __shfl_xor_sync(0xffffffffu, lb, m);
+                const int oj = __shfl_xor_sync(0xffffffffu, jb, m);
+                if (ol < lb || (ol == lb && oj < jb)) { lb = ol; jb = oj; }
+            }
+            if (lb < INFINITY && jb != jm) {
+                const double w2 = probe(jb, row[jb]);
+                if (w2 < w || !(w == w)) w = w2;
+                if (w < kPruneMaxWeight) thr2 = threshold(w);
+            }
+        }
+        // second test: out when  qa d^2 - (head excess)  >  slack, i.e. when
+        // (qa d^2 + qc) - (S L + head excess + tail bound) > W ln 10  (the qb d term of the
+        // parabola, >= 0, is dropped: no sqrt per pair)
+        double slack = INFINITY;
+        if (w < kPruneMaxWeight)
+            slack = w * (1.0 + 1e-9) * c_gauss.ln10 + sl + u_tail * (1.0 + 1e-9) - c_math.prune_c;
+        // the candidates, in bin order; a NaN distance stays in
+        int count = 0;
+        for (int sb = 0; sb < n_slabs; ++sb) {
+            const int j = 32 * sb + lane;
+            const double dd = j < B.n ? row[j] : INFINITY;
+            bool keep = j < B.n && !(dd > thr2);
+            // prob_comp is exactly 0 from d = 0.2003 on (exp underflow, log_comp_prob_special):
+            // the weight is MAX_WEIGHT, which never wins and means None when nothing else is
+            // left.  Beyond d^2 = 1.5 the reference's own sequence decides (domain errors): kept.
+            if (dd > 0.0405 && dd < 1.5) keep = false;
+            if (slack < INFINITY && __any_sync(0xffffffffu, keep)) {
+                double e1 = 0.0;
+                const double *hp = head + (j < B.n ? j : 0);
+#pragma unroll 4
+                for (int q = 0; q < nq; ++q) {
+                    const double bc = hp[(2 * q) * ldh], bl = hp[(2 * q + 1) * ldh];
+                    add_poisson_excess(e1, HA[wid][2 * q], HA[wid][2 * q + 1], bc, bl);
+                }
+                const double lhs = fma(c_math.prune_4a * 0.25, dd, -e1 * (1.0 + 1e-9));
+                if (lhs > slack) keep = false;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) MASK[wid][sb] = mask;
+            count += __popc(mask);
+        }
+        int base = 0;
+        if (lane == 0) {
+            base = atomicAdd(cl.total, count);
+            cl.start[r] = base;
+            cl.count[r] = count;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        if (base + count <= cl.cap) {
+            int at = base;
+            for (int sb = 0; sb < n_slabs; ++sb) {
+                const unsigned mask = MASK[wid][sb];
+                if ((mask >> lane) & 1u)
+                    cl.pair[at + __popc(mask & ((1u << lane) - 1u))] =
+                        make_int2(static_cast<int>(r), 32 * sb + lane);
+                at += __popc(mask);
+            }
+        }
+    }
+}
+
+// One thread per listed pair: the weight prob_kernel computes for it, operation for operation
+// (log_comp_prob_warp, excess sums in sample order, the e^-744 / e^-746 window, the GUARD
+// deferral); NaN marks a deferred pair.
+template <bool GUARD>
+__global__ void __launch_bounds__(256)
+cand_score_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
+                  CandList cl, int32_t *__restrict__ status) {
+    __shared__ double ET[16];
+    __shared__ double LT[128];
+    const int tid = threadIdx.x;
+    if (tid < 16) ET[tid] = g_exp_table[tid];
+    if (tid < 128) LT[tid] = g_log_table[tid];
+    __syncthreads();
+    const int total = *cl.total;
+    if (total > cl.cap) return;
+    const int stride = gridDim.x * blockDim.x;
+    const int padded = (total + 31) & ~31;   // whole warps: log_comp_prob_warp votes
+    for (int i = blockIdx.x * blockDim.x + tid; i < padded; i += stride) {
+        const bool live = i < total;
+        const int2 pr = live ? cl.pair[i] : make_int2(0, 0);
+        const double dd = d2[pr.x * ldc + pr.y];
+        const double log_pc = log_comp_prob_warp(dd, ET, LT, status);
+        double tsum = log_pc;
+        bool defer = false;
+        if (log_pc == log_pc) {
+            const long long arow = A.index ? A.index[A.first + pr.x] : (A.first + pr.x);
+            const long long brow = B.index ? B.index[B.first + pr.y] : (B.first + pr.y);
+            const double *ac_p = A.cov + arow * S, *al_p = A.logc + arow * S, *ag_p = A.lgam + arow * S;
+            const double *bc_p = B.cov + brow * S, *bl_p = B.logc + brow * S, *bg_p = B.lgam + brow * S;
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll 2
+            for (int q = 0; q < S; ++q) {
+                const double ac = ac_p[q], al = al_p[q], am = -(ag_p[q] + c_math.log_floor);
+                const double bc = bc_p[q], bl = bl_p[q], bm = -(bg_p[q] + c_math.log_floor);
+                add_poisson_excess(s1, ac, am, bc, bl);
+                add_poisson_excess(s2, bc, bm, ac, al);
+            }
+            const double pmin = fma(static_cast<double>(S), c_math.log_floor, s1 < s2 ? s1 : s2);
+            tsum = log_pc + pmin;
+            if (GUARD) defer = pmin < kGuardLog;
+        }
+        bool valid = tsum > -744.0;
+        if (!valid && tsum >= -746.0)
+            valid = __dmul_rn(exp_slow(log_pc), exp_slow(tsum - log_pc)) > 0.0;
+        const double lp = -tsum * c_math.inv_ln10;
+        const double w = (valid && lp != 0.0) ? lp : MCG_MAX_WEIGHT;
+        if (live) cl.w[i] = defer ? __longlong_as_double(0x7ff8000000000000LL) : w;
+    }
+}
+
+// First minimum of a contig's candidates and the bookkeeping of prob_kernel's last bin group.
+template <bool GUARD>
+__global__ void __launch_bounds__(256)
+cand_argmin_kernel(ScoreSide A, CandList cl, ScoreOut out, RedoList redo) {
+    if (*cl.total > cl.cap) return;
+    const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (r >= A.n) return;
+    const int lo = cl.start[r], hi = lo + cl.count[r];
+    double bw = 0.0;
+    int bi = -1;
+    bool def = false;
+    for (int i = lo; i < hi; ++i) {
+        const double w = cl.w[i];
+        if (w != w) { def = true; continue; }
+        if (bi < 0 || w < bw) { bw = w; bi = cl.pair[i].y; }
+    }
+    const bool none = (bi < 0) || (bw == MCG_MAX_WEIGHT);   // label_prop_utils.py:342-345
+    if (out.argmin) out.argmin[A.first + r] = none ? -1 : bi;
+    if (out.wmin) out.wmin[A.first + r] = none ? MCG_MAX_WEIGHT : bw;
+    if (GUARD && def && (none || !(bw < kGuardWeight))) {
+        const int slot = atomicAdd(redo.count, 1);
+        redo.rows[slot] = A.index ? A.index[A.first + r] : (A.first + r);
+        redo.pos[slot] = A.first + r;
     }
 }
 
@@ -1286,6 +1587,13 @@ static int ensure_gauss(mcg_ctx *ctx) {
     m.log_inv_denom_intra = -log(g.denom_intra);
     m.sd_ratio = sd_i / sd_e;
     m.log_sd_ratio = log(sd_i / sd_e);
+    {
+        const double k1 = m.inv_two_var_intra, k2 = m.inv_two_var_inter, mu = g.mu_inter;
+        m.prune_4a = 4.0 * (k1 - k2);
+        m.prune_b = 2.0 * mu * k2;
+        m.prune_c = m.log_sd_ratio - mu * mu * k2;
+        m.prune_inv_2a = 1.0 / (2.0 * (k1 - k2));
+    }
     MCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_math, &m, sizeof m, 0, cudaMemcpyHostToDevice,
                                           ctx->stream));
     MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1333,6 +1641,8 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
                         const ScoreOut &out, int32_t *d_status) {
     static bool attr[64] = {};
     const bool guard = S > 30;
+    // the full weight matrix needs every pair; the argmin does not (bound_kernel)
+    const bool use_cand = ctx->prune && !out.weights && b.n <= 32LL * kMaxSlabs;
     const long long b_tiles = (b.n + kTile - 1) / kTile;
     const long long ldc = b_tiles * kTile;
     // bins per shared-memory group of prob_kernel, whole warps of columns: S <= 30 keeps the
@@ -1392,6 +1702,31 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         MCG_CUDA(ctx, cudaMemsetAsync(redo.count, 0, 16, ctx->stream));
     }
     ctx->redo_valid = guard;
+    CandList cl = {nullptr, 0, nullptr, nullptr, nullptr, nullptr};
+    ctx->cand_valid = false;
+    if (use_cand) {
+        // [total | pad] [start rows] [count rows] [pair cap] [w cap]
+        long long cap = need_rows * ldc / 4;
+        if (cap > 0x3fffffffLL) cap = 0x3fffffffLL;
+        if (cap < 1024) cap = 1024;
+        const size_t bytes = 16 + static_cast<size_t>(need_rows) * 8 + static_cast<size_t>(cap) * 16;
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[3], bytes));
+        char *base = ctx->scratch[3].as<char>();
+        cl.total = reinterpret_cast<int *>(base);
+        cl.cap = static_cast<int>(cap);
+        cl.start = reinterpret_cast<int *>(base + 16);
+        cl.count = cl.start + need_rows;
+        cl.pair = reinterpret_cast<int2 *>(cl.count + need_rows);
+        cl.w = reinterpret_cast<double *>(cl.pair + cap);
+        ctx->cand_valid = true;
+        ctx->cand_cap = cap;
+        const int nq = S < kHeadSamples ? S : kHeadSamples;
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(double) * 2 * nq * ldc));
+        bin_head_kernel<<<blocks_for(b.n * nq, 256), 256, 0, ctx->stream>>>(
+            b, S, nq, ldc, ctx->scratch[1].as<double>());
+        MCG_KERNEL_CHECK(ctx);
+    }
+    const CandGate gate = {cl.total, cl.cap};
     ScoreOut shifted = out;   // outputs are indexed by (first + r): shift them back
     shifted.argmin = out.argmin - a.first;
     shifted.wmin = out.wmin - a.first;
@@ -1413,21 +1748,43 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         const long long cap = 4LL * ctx->sm_count * 4;
         if (blocks > cap) blocks = cap;
         mcg_timer_begin(ctx, T_PROB);
+        if (use_cand) {
+            ctx->cand_pairs = ac.n * b.n;
+            MCG_CUDA(ctx, cudaMemsetAsync(cl.total, 0, 16, ctx->stream));
+            long long bb = (ac.n + 7) / 8;
+            if (bb > 8LL * ctx->sm_count) bb = 8LL * ctx->sm_count;
+            bound_kernel<<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
+                ac, b, S, d2, ldc, ctx->scratch[1].as<double>(), ldc, cl, d_status);
+            MCG_KERNEL_CHECK(ctx);
+            const unsigned sb = static_cast<unsigned>(8 * ctx->sm_count);
+            if (guard) {
+                cand_score_kernel<true><<<sb, 256, 0, ctx->stream>>>(ac, b, S, d2, ldc, cl, d_status);
+                MCG_KERNEL_CHECK(ctx);
+                cand_argmin_kernel<true><<<blocks_for(ac.n, 256), 256, 0, ctx->stream>>>(
+                    ac, cl, shifted, redo);
+            } else {
+                cand_score_kernel<false><<<sb, 256, 0, ctx->stream>>>(ac, b, S, d2, ldc, cl, d_status);
+                MCG_KERNEL_CHECK(ctx);
+                cand_argmin_kernel<false><<<blocks_for(ac.n, 256), 256, 0, ctx->stream>>>(
+                    ac, cl, shifted, redo);
+            }
+            MCG_KERNEL_CHECK(ctx);
+        }
         for (long long g0 = 0; g0 < b.n; g0 += group) {
             const int ncols = static_cast<int>(b.n - g0 < group ? b.n - g0 : group);
             const int ncols_pad = (ncols + 31) / 32 * 32;
             const size_t smem_g = prob_smem - sizeof(double) * pitch * (group - ncols);
             if (guard && warps == 16)
                 prob_kernel<true, 16><<<static_cast<unsigned>(blocks), 512, smem_g, ctx->stream>>>(
-                    ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch, shifted, d_status, redo);
+                    ac, b, S, d2, ldc, g0, ncols, ncols_pad, pitch, shifted, d_status, redo, gate);
             else if (guard)
                 prob_kernel<true, 8><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
                                        ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad,
-                                                      pitch, shifted, d_status, redo);
+                                                      pitch, shifted, d_status, redo, gate);
             else
                 prob_kernel<false, 8><<<static_cast<unsigned>(blocks), kProbThreads, smem_g,
                                         ctx->stream>>>(ac, b, S, d2, ldc, g0, ncols, ncols_pad,
-                                                       pitch, shifted, d_status, redo);
+                                                       pitch, shifted, d_status, redo, gate);
             MCG_KERNEL_CHECK(ctx);
         }
         // (the timer holds one interval: with S > 30 it closes after the redo pass below)
@@ -1585,5 +1942,22 @@ int mcg_k_fp64_peak(mcg_ctx *ctx, double *tflops) {
     cudaEventDestroy(e1);
     const double flops = 2.0 * 64.0 * iters * static_cast<double>(blocks) * threads;
     *tflops = flops / (best * 1e-3) / 1e12;
+    return MCG_OK;
+}
+
+// The candidate list of the last rule-C chunk (bound_kernel): [0] pairs listed, [1] capacity of
+// the list, [2] all pairs of the chunk, [3] 1 when the list was used (0: it overflowed and
+// prob_kernel scored every pair, or pruning was off).
+int mcg_k_prune_stats(mcg_ctx *ctx, int64_t stats[4]) {
+    for (int i = 0; i < 4; ++i) stats[i] = 0;
+    if (!ctx->cand_valid) return MCG_OK;
+    int32_t total = 0;
+    MCG_CUDA(ctx, cudaMemcpyAsync(&total, ctx->scratch[3].p, sizeof total, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    MCG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    stats[0] = total;
+    stats[1] = ctx->cand_cap;
+    stats[2] = ctx->cand_pairs;
+    stats[3] = total <= ctx->cand_cap ? 1 : 0;
     return MCG_OK;
 }

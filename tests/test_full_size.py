@@ -59,6 +59,10 @@ def check_scoring(ctx, tabs, blob, n_oracle, seed):
     ctx.load_coverage(cov)
     cen_prof, cen_cov = ctx.bin_profiles(tabs["members"], tabs["seg"])
     arg, w, _ = ctx.score_centroids(cen_prof=cen_prof, cen_cov=cen_cov)
+    ctx.set_prune(False)      # every pair scored: not a bit may differ (tests/test_prune.py)
+    arg_all, w_all, _ = ctx.score_centroids(cen_prof=cen_prof, cen_cov=cen_cov)
+    ctx.set_prune(True)
+    assert np.array_equal(arg, arg_all) and np.array_equal(w, w_all)
     assert arg.shape == (n,) and (arg >= -1).all() and (arg < cen_prof.shape[0]).all()
     assert np.array_equal(w == MAXW, arg == -1)
 
