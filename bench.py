@@ -359,6 +359,7 @@ def main():
     drain()
     torch.cuda.synchronize()
     assert torch.equal(all_pairs_arg, d_argmin) and torch.equal(all_pairs_w, d_wmin)
+    prune_stats = ctx.prune_stats()
     ctx.profile(False)
     barrier()
 
@@ -525,8 +526,11 @@ def main():
         "kernel_ms": kernel_ms,
         "kernel_ms_every_pair_scored": kernel_ms_all,
     }
-    line["config"]["rule_c"] = ("branch and bound on -log10 prob_comp (exact: argmin and weights "
-                                "checked equal to the all-pairs pass in this run)")
+    line["config"]["rule_c"] = ("branch and bound (bound_kernel + candidate kernels; exact: argmin "
+                                "and weights checked bit-equal to the all-pairs pass in this run)")
+    line["rule_c_candidates"] = dict(prune_stats, note="pairs scored after the bound / all pairs "
+                                     "of the last rule-C chunk; used = the candidate list held "
+                                     "them all (else prob_kernel scores every pair)")
     if N_SAMPLES > 30:
         # contigs the guarded rule-C path re-scored in the reference's operation order
         line["config"]["redo_contigs_per_step"] = int(ctx.last_redo_count())
