@@ -103,6 +103,11 @@ int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads);
  * (label_prop_utils.py:340-345, first minimum) are the same bits with and without.  On by
  * default; 0 scores every pair (measurement, tests). */
 int mcg_set_prune(mcg_ctx *ctx, int enabled);
+/* The scan kernel is persistent, one CTA per SM, and its shared memory leaves no room for
+ * another kernel's CTA: a collective launched on another stream (the NCCL broadcast of the bin
+ * tables, the all-gather of the assignments) would start only when the scan ends.  This keeps
+ * `sms` SMs out of the scan's grid so that it starts at once (multi-GPU callers: 2-4). */
+int mcg_set_reserved_sms(mcg_ctx *ctx, int sms);
 /* The last pruned rule-C chunk (synchronises the stream): [0] pairs listed as candidates,
  * [1] capacity of the list, [2] all pairs of the chunk, [3] 1 when the list was used, 0 when it
  * overflowed and every pair was scored (or pruning is off). */

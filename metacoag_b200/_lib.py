@@ -72,6 +72,7 @@ SIGNATURES = {
     "mcg_last_redo_count": (_int, [_vp, _vp]),
     "mcg_set_host_pack_threads": (_int, [_vp, _int]),
     "mcg_set_prune": (_int, [_vp, _int]),
+    "mcg_set_reserved_sms": (_int, [_vp, _int]),
     "mcg_prune_stats": (_int, [_vp, _vp]),
     "mcg_ingest_stats": (_int, [_vp, _vp]),
     "mcg_pack_2bit_host": (_int, [_vp, _vp, _i64, _vp, _int]),
@@ -246,6 +247,10 @@ class Context:
     def set_prune(self, enabled):
         """Rule-C branch and bound on / off (include/mcg_b200.h); results do not change."""
         self._check(self.lib.mcg_set_prune(self.handle, int(bool(enabled))))
+
+    def set_reserved_sms(self, sms):
+        """SMs the persistent scan kernel leaves free for collectives on another stream."""
+        self._check(self.lib.mcg_set_reserved_sms(self.handle, int(sms)))
 
     def prune_stats(self):
         """The candidate list of the last pruned rule-C chunk (include/mcg_b200.h)."""

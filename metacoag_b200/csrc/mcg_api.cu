@@ -142,6 +142,7 @@ extern "C" mcg_ctx *mcg_create(int device) {
     }
     mcg_ctx *ctx = new mcg_ctx();
     ctx->device = device;
+    if (const char *env = getenv("MCG_PRUNE")) ctx->prune = atoi(env) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1404,6 +1405,13 @@ extern "C" int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, 
 extern "C" int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads) {
     MCG_ENTER(ctx);
     ctx->host_pack_threads = threads;
+    return MCG_OK;
+}
+
+extern "C" int mcg_set_reserved_sms(mcg_ctx *ctx, int sms) {
+    MCG_ENTER(ctx);
+    if (sms < 0 || sms >= ctx->sm_count) return mcg_fail(ctx, MCG_ERR_ARG, "bad SM count");
+    ctx->reserved_sms = sms;
     return MCG_OK;
 }
 

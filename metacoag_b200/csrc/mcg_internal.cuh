@@ -42,6 +42,7 @@ struct mcg_ctx {
     cudaEvent_t copy2_done = nullptr;
     void *pinned_pack = nullptr;          // host-packed contigs, staged for the copy engine
     size_t pinned_pack_cap = 0;
+    int reserved_sms = 0;                 // SMs the persistent scan leaves free (mcg_set_reserved_sms)
     int prune = 1;                        // rule-C branch and bound (mcg_set_prune)
     int host_pack_threads = -1;           // -1: MCG_HOST_PACK_THREADS or the hardware threads - 1
     int64_t ingest_stats[4] = {};         // last ASCII load: h2d bytes, host-packed bases,

@@ -495,7 +495,11 @@ int mcg_k_scan_range(mcg_ctx *ctx, const uint32_t *d_packed, const ContigMeta *d
         if (ctx->device < 64) attr_set[ctx->device] = true;
     }
     const int64_t n_tiles = (seg1 - seg0 + 31) / 32;
-    int64_t grid = static_cast<int64_t>(ctx->sm_count) * kScanCtasPerSm;
+    // the scan CTAs are persistent and fill an SM each (shared memory): SMs left free let a
+    // collective on another stream start under the scan instead of behind it
+    int sms = ctx->sm_count - ctx->reserved_sms;
+    if (sms < 1) sms = 1;
+    int64_t grid = static_cast<int64_t>(sms) * kScanCtasPerSm;
     const int64_t need = (n_tiles + kScanWarps - 1) / kScanWarps;
     if (grid > need) grid = need;
     scan_kernel<<<static_cast<unsigned>(grid), kScanThreads, smem, ctx->stream>>>(
