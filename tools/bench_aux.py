@@ -120,8 +120,70 @@ def main():
                                    "cpu_ms_python_dfs_labelling": cpu_s * 1e3,
                                    "reference_style_sweep_s_for_one_start_capped_at_4000_vertices": ref_s}
 
-    # ---- bin x bin merge matrix --------------------------------------------------------------------
+    # ---- label propagation candidates: bounded BFS + rule B ----------
+    # one stage of label_prop: every unlabelled long contig walks to the labelled contigs within
+    # `depth` (label_prop_utils.py:24-53, 92-100) and is scored against the seed members of every
+    # bin it reached (:54-86).  CPU side: the reference's BFS restated in Python (ref_bfs) and the
+    # C port of rule B, both on a sample.
+    from oracle_backend import ref_bfs
     from oracle import oracle
+    B, S = 200, 10
+    import bench
+    bench.LENGTH_KIND = "megahit"
+    tabs = bench.workload_tables(11, n, S, B)
+    lp_blob = ctx.synth_bases(tabs["offsets"], tabs["genome_of"], tabs["trans"], 11)
+    rngl = np.random.default_rng(12)
+    genome = np.asarray(tabs["genome_of"])
+    labels = np.where(rngl.random(n) < 0.3, genome, -1).astype(np.int32)
+    starts = np.flatnonzero(labels < 0)[:40000].astype(np.int64)
+    ctx.bfs_candidates(indptr, indices, labels, starts[:64], 10)
+    t0 = time.perf_counter()
+    node, bin_, depth, n_hits = ctx.bfs_candidates(indptr, indices, labels, starts, 10)
+    bfs_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    k = 0
+    for i in range(0, starts.shape[0], starts.shape[0] // 200):
+        want = ref_bfs(int(starts[i]), 10, labels, indptr, indices)
+        got = [(int(node[i, h]), int(bin_[i, h]), int(depth[i, h])) for h in range(int(n_hits[i]))]
+        assert got == want, (i, got[:3], want[:3])
+        k += 1
+    bfs_cpu = (time.perf_counter() - t0) / k
+    # rule B of every start node against 20 seed members per bin
+    ctx.load_contigs(lp_blob, tabs["offsets"])
+    ctx.scan()
+    cov = np.maximum(tabs["coverage"], 1e-4)
+    ctx.load_coverage(cov)
+    order = np.argsort(genome, kind="stable")
+    first = np.searchsorted(genome[order], np.arange(B + 1))
+    members = np.concatenate([order[first[b]:first[b + 1]][:20] for b in range(B)]).astype(np.int64)
+    seg = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum([min(20, first[b + 1] - first[b]) for b in range(B)], out=seg[1:])
+    keep = np.flatnonzero(np.diff(seg) > 0)
+    seg = np.concatenate([[0], seg[1:][keep]]).astype(np.int64)
+    ctx.score_members(starts, members, seg, _lib.RULE_B)      # sizes the device buffers
+    t0 = time.perf_counter()
+    wB = ctx.score_members(starts, members, seg, _lib.RULE_B)
+    ruleb_s = time.perf_counter() - t0
+    prof_h = ctx.get_profiles()
+    pick = starts[:: starts.shape[0] // 40]
+    t0 = time.perf_counter()
+    want = oracle.score_members(prof_h, cov, pick, members, seg, _lib.RULE_B, nthreads=1)
+    ruleb_cpu = (time.perf_counter() - t0) / (pick.shape[0] * members.shape[0])
+    got = wB[:: starts.shape[0] // 40]
+    same = (want == _lib.MAX_WEIGHT) | (got == _lib.MAX_WEIGHT)
+    assert np.array_equal(want[same], got[same])
+    assert (np.abs(got[~same] - want[~same]) / np.abs(want[~same])).max() <= 1e-9
+    out["label_prop_candidates"] = {
+        "vertices": n, "labelled": int((labels >= 0).sum()), "start_nodes": int(starts.shape[0]),
+        "depth": 10, "hits": int(n_hits.sum()),
+        "bfs_gpu_ms_total_incl_copies": bfs_s * 1e3, "bfs_gpu_us_per_start": bfs_s * 1e6 / starts.shape[0],
+        "bfs_cpu_us_per_start_python": bfs_cpu * 1e6,
+        "rule_b_pairs": int(starts.shape[0] * members.shape[0]),
+        "rule_b_gpu_ms_total_incl_copies": ruleb_s * 1e3,
+        "rule_b_gpu_ns_per_pair": ruleb_s * 1e9 / (starts.shape[0] * members.shape[0]),
+        "rule_b_cpu_ns_per_pair_c_port_1_thread": ruleb_cpu * 1e9}
+
+    # ---- bin x bin merge matrix --------------------------------------------------------------------
     for B, S in ((200, 10), (1000, 100)):
         asm = synth.make_assembly(seed=B, n_genomes=B, n_contigs=B, n_samples=S,
                                   length_kind="spades", with_graph=False, with_markers=False)
