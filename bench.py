@@ -43,11 +43,15 @@ WORKLOAD = "synthetic %s-style %dk contigs, %d samples, %d bins per GPU" % (
 METRIC = "contigs/sec featurise+score"
 
 
-def workload_tables(seed, n_contigs, n_samples, n_bins):
-    """Everything of the synthetic data set except the bases."""
+def workload_tables(seed, n_contigs, n_samples, n_bins, shard=0):
+    """Everything of the synthetic data set except the bases.  The
+    community (genome composition and abundance tables) depends on ``seed`` only; ``shard`` > 0
+    draws another set of contigs from the same community (the rows of another rank)."""
     from metacoag_b200 import synth
     rng = np.random.default_rng(seed)
     dinuc, abundance = synth.genome_tables(rng, n_bins, n_samples)
+    if shard:
+        rng = np.random.default_rng([seed, shard])
     trans = dinuc.reshape(n_bins, 4, 4)
     trans = (trans / trans.sum(axis=2, keepdims=True)).astype(np.float32)
     lengths = synth.sample_lengths(rng, n_contigs, LENGTH_KIND)
@@ -257,8 +261,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- setup (untimed) ---------------------------------------------------------------
+    # every rank draws its own contigs from the SAME community (the bins rank 0 broadcasts are
+    # the bins of all shards); until round 1h ranks > 0 drew their own community, so their contigs
+    # matched no bin and their scorer ran 0.2 ms longer than rank 0's
     seed = 1001 + rank
-    tabs = workload_tables(seed, N_CONTIGS, N_SAMPLES, N_BINS)
+    tabs = workload_tables(1001, N_CONTIGS, N_SAMPLES, N_BINS, shard=rank)
     offsets, coverage = tabs["offsets"], tabs["coverage"]
     n, n_bases = N_CONTIGS, int(offsets[-1])
     ctx = _lib.Context(local)
@@ -304,12 +311,31 @@ def main():
     gathered = [None]
     step_no = [0]
 
+    exp = os.environ.get("MCG_BENCH_EXP", "")     # timing experiments only (not a bench line)
+
+    # Peer-memory exchange (NVLink / NVSwitch stores + a signal-pad barrier, all on the compute
+    # stream) when the GPUs can map each other's memory; the NCCL collectives otherwise.
+    peer = None
+    if world > 1 and os.environ.get("MCG_BENCH_EXCHANGE", "peer") == "peer":
+        try:
+            peer = parallel.PeerExchange(n, N_BINS, N_SAMPLES, dev)
+        except Exception as err:   # no peer access on this box
+            print("peer exchange unavailable (%s): NCCL collectives" % err, file=sys.stderr)
+            peer = None
+
     def issue_broadcast(k):
         """Centroid tables of step k into buffer k & 1, on the collective stream."""
+        if "nocoll" in exp:
+            return
         q = k & 1
         with torch.cuda.stream(comm):
             comm.wait_event(ev_scored[q])       # the scorer of step k - 2 read these tables
-            parallel.broadcast_centroids(cen_bufs[q][0], cen_bufs[q][1], src=0)
+            if peer is not None:
+                if rank == 0:
+                    peer.push_centroids(ctx, q, d_cen_prof, d_cen_cov, stream=comm)
+                peer.barrier(channel=0)
+            else:
+                parallel.broadcast_centroids(cen_bufs[q][0], cen_bufs[q][1], src=0)
             ev_bcast[q].record(comm)
 
     def step():
@@ -319,22 +345,32 @@ def main():
         k = step_no[0]
         step_no[0] += 1
         par = k & 1
-        cp, cc = cen_bufs[par]
+        cp, cc = peer.centroids(par) if peer is not None else cen_bufs[par]
         oa, ow = out_bufs[par]
         if k == 0:
             issue_broadcast(0)
         ctx.step_featurise()
-        # the tables of the NEXT step are broadcast now: the collective is queued in front of this
-        # step's all-gather and runs under the scorer (the persistent scan leaves no SM for it)
+        # the tables of the NEXT step are sent now: the exchange is queued in front of this step's
+        # gather and runs under the scorer.  (Why overwriting parity (k + 1) & 1 is safe: the
+        # gather of step k - 1, in front of it on the collective stream, ends with a rendezvous
+        # every rank reaches after its scorer of step k - 1, the last reader of those tables.)
         issue_broadcast(k + 1)
         stream.wait_event(ev_bcast[par])
-        stream.wait_event(ev_gathered[par])     # the gather two steps back read these buffers
-        ctx.set_centroids_dev(cp.data_ptr(), cc.data_ptr(), N_BINS)
+        stream.wait_event(ev_gathered[par])     # the exchange two steps back read these buffers
+        if "nosetcen" not in exp:
+            ctx.set_centroids_dev(cp.data_ptr(), cc.data_ptr(), N_BINS)
         ctx.step_score(oa.data_ptr(), ow.data_ptr())
         ev_scored[par].record(stream)
+        if "nocoll" in exp:
+            return oa, ow
         with torch.cuda.stream(comm):
             comm.wait_event(ev_scored[par])
-            gathered[0] = parallel.gather_assignments(oa, ow, counts=[n] * world)
+            if peer is not None:
+                peer.push_assignments(ctx, par, oa, ow, stream=comm)
+                peer.barrier(channel=1)
+                gathered[0] = peer.assignments(par)
+            else:
+                gathered[0] = parallel.gather_assignments(oa, ow, counts=[n] * world)
             ev_gathered[par].record(comm)
         return gathered[0]
 
@@ -346,6 +382,16 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    if peer is not None:
+        # the gathered arrays the peer stores built == what the NCCL all-gather builds
+        got_a, got_w = step()
+        drain()
+        torch.cuda.synchronize()
+        last = out_bufs[(step_no[0] - 1) & 1]
+        want_a, want_w = parallel.gather_assignments(last[0], last[1], counts=[n] * world)
+        torch.cuda.synchronize()
+        assert torch.equal(got_a, want_a) and torch.equal(got_w, want_w)
+        barrier()
 
     # ---- per-kernel device times (CUDA events on the launching stream) ------------------
     ctx.profile(True)
@@ -531,7 +577,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "contigs_per_gpu": n, "bases_per_gpu": n_bases,
                    "samples": N_SAMPLES, "bins": N_BINS,
-                   "parallelism": "row-sharded x%d, NCCL broadcast + all-gather" % world,
+                   "parallelism": ("row-sharded x%d, " % world) +
+                                  ("bin tables and assignments exchanged by peer-memory stores "
+                                   "(NVLink) + signal barrier" if peer is not None
+                                   else "NCCL broadcast + all-gather"),
                    "l2": "inputs larger than L2 (%.0f MB packed bases + %.0f MB profiles per step)"
                          % (n_bases / 4e6, n * 136 * 8 / 1e6)},
         "clocks": clocks,

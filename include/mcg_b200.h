@@ -108,6 +108,16 @@ int mcg_set_prune(mcg_ctx *ctx, int enabled);
  * tables, the all-gather of the assignments) would start only when the scan ends.  This keeps
  * `sms` SMs out of the scan's grid so that it starts at once (multi-GPU callers: 2-4). */
 int mcg_set_reserved_sms(mcg_ctx *ctx, int sms);
+/* The exchange steps of the path (bin tables from rank 0 to every rank, per-contig
+ * (bin, weight) from every rank to every rank) as stores into peer memory: the caller maps one
+ * buffer per rank into every process (symmetric memory: CUDA VMM / IPC; metacoag_b200/parallel.py
+ * uses torch's allocator for it) and passes, per rank, the address where this rank's block goes.
+ * One kernel on `stream` writes `bytes` (a multiple of 4) from d_src to all `world`
+ * destinations over NVLink / NVSwitch; 16-byte stores when all addresses and the size allow.
+ * Arrival is the caller's business (a barrier over the same symmetric allocation). */
+#define MCG_MAX_PEERS 16
+int mcg_push_to_peers(mcg_ctx *ctx, const void *d_src, size_t bytes, void *const *peer_dst,
+                      int world, void *stream /* cudaStream_t; NULL = the context's stream */);
 /* The last pruned rule-C chunk (synchronises the stream): [0] pairs listed as candidates,
  * [1] capacity of the list, [2] all pairs of the chunk, [3] 1 when the list was used, 0 when it
  * overflowed and every pair was scored (or pruning is off). */

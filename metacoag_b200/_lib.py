@@ -73,6 +73,7 @@ SIGNATURES = {
     "mcg_set_host_pack_threads": (_int, [_vp, _int]),
     "mcg_set_prune": (_int, [_vp, _int]),
     "mcg_set_reserved_sms": (_int, [_vp, _int]),
+    "mcg_push_to_peers": (_int, [_vp, _vp, _c.c_size_t, _vp, _int, _vp]),
     "mcg_prune_stats": (_int, [_vp, _vp]),
     "mcg_ingest_stats": (_int, [_vp, _vp]),
     "mcg_pack_2bit_host": (_int, [_vp, _vp, _i64, _vp, _int]),
@@ -251,6 +252,14 @@ class Context:
     def set_reserved_sms(self, sms):
         """SMs the persistent scan kernel leaves free for collectives on another stream."""
         self._check(self.lib.mcg_set_reserved_sms(self.handle, int(sms)))
+
+    def push_to_peers(self, src_ptr, nbytes, peer_ptrs, stream=None):
+        """``nbytes`` from device address ``src_ptr`` to every address of ``peer_ptrs`` (peer
+        memory mapped into this process), one kernel on ``stream`` (a cudaStream_t handle;
+        default: the context's stream)."""
+        arr = (_c.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._check(self.lib.mcg_push_to_peers(self.handle, int(src_ptr), int(nbytes), arr,
+                                               len(peer_ptrs), stream))
 
     def prune_stats(self):
         """The candidate list of the last pruned rule-C chunk (include/mcg_b200.h)."""

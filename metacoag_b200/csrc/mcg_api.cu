@@ -1408,6 +1408,55 @@ extern "C" int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads) {
     return MCG_OK;
 }
 
+// ---- multi-GPU exchange over peer memory ---------------------------------------------------------
+// The two exchange steps of the path (bin tables from rank 0, per-contig results to
+// every rank) are small against NVLink 5 and latency-bound as NCCL collectives.  With every
+// rank's buffer mapped into every process (symmetric memory: CUDA VMM / IPC handles, here
+// obtained by the caller), they are plain stores: one kernel on the compute stream writes the
+// local block into the same place of every peer's buffer, through NVLink / NVSwitch.
+struct PeerDst {
+    void *p[MCG_MAX_PEERS];
+};
+
+template <typename T>
+__global__ void push_to_peers_kernel(const T *__restrict__ src, PeerDst dst, int world,
+                                     size_t count) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count;
+         i += stride) {
+        const T v = src[i];
+        for (int r = 0; r < world; ++r) static_cast<T *>(dst.p[r])[i] = v;
+    }
+}
+
+extern "C" int mcg_push_to_peers(mcg_ctx *ctx, const void *d_src, size_t bytes,
+                                 void *const *peer_dst, int world, void *stream) {
+    MCG_ENTER(ctx);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (!d_src || !peer_dst || world < 1 || world > MCG_MAX_PEERS || (bytes & 3))
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad peer push arguments");
+    if (bytes == 0) return MCG_OK;
+    PeerDst dst;
+    bool aligned = (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (bytes & 15) == 0;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_dst[r]) return mcg_fail(ctx, MCG_ERR_ARG, "peer %d has no buffer", r);
+        dst.p[r] = peer_dst[r];
+        aligned = aligned && (reinterpret_cast<uintptr_t>(peer_dst[r]) & 15) == 0;
+    }
+    const int threads = 256;
+    const size_t count = aligned ? bytes / 16 : bytes / 4;   // 16-byte stores when everything allows it
+    size_t blocks = (count + threads - 1) / threads;
+    if (blocks > static_cast<size_t>(4 * ctx->sm_count)) blocks = 4 * ctx->sm_count;
+    if (aligned)
+        push_to_peers_kernel<uint4><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+            static_cast<const uint4 *>(d_src), dst, world, count);
+    else
+        push_to_peers_kernel<uint32_t><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+            static_cast<const uint32_t *>(d_src), dst, world, count);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
 extern "C" int mcg_set_reserved_sms(mcg_ctx *ctx, int sms) {
     MCG_ENTER(ctx);
     if (sms < 0 || sms >= ctx->sm_count) return mcg_fail(ctx, MCG_ERR_ARG, "bad SM count");

@@ -149,3 +149,79 @@ def all_gather_rows(ints, floats):
     stats["sharded_calls"] += 1
     stats["rows_gathered"] += int(keep.shape[0])
     return out_i[keep], out_f[keep]
+
+
+class PeerExchange:
+    """The two exchange steps of the path as stores into peer memory (NVLink / NVSwitch)
+    instead of NCCL collectives: every rank owns one symmetric buffer (torch's symmetric-memory
+    allocator: CUDA VMM handles exchanged at rendezvous, every peer's buffer mapped into every
+    process) holding, per step parity, the gathered assignments of all ranks and the bin
+    tables.  ``push_*`` launch ``mcg_push_to_peers`` on the library's stream; ``barrier`` (the
+    allocation's signal pads, a few microseconds) tells everyone the blocks have landed.
+
+    Raises when symmetric memory cannot be set up (no peer access between the GPUs): callers
+    fall back to ``broadcast_centroids`` / ``gather_assignments``.
+    """
+
+    def __init__(self, rows_per_rank, n_bins, n_samples, device):
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.rows = int(rows_per_rank)
+        self.n_bins, self.n_samples = int(n_bins), int(n_samples)
+
+        def up(x):
+            return (x + 255) // 256 * 256
+        total = self.world * self.rows
+        self.off_arg = 0
+        self.off_w = up(4 * total)
+        self.off_prof = self.off_w + up(8 * total)
+        self.off_cov = self.off_prof + up(8 * 136 * self.n_bins)
+        self.slot = self.off_cov + up(8 * self.n_samples * self.n_bins)
+        self.buf = symm.empty(2 * self.slot, dtype=torch.uint8, device=device)
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.ptrs) != self.world or not all(self.ptrs):
+            raise RuntimeError("symmetric memory rendezvous gave no peer pointers")
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        self.handle.barrier(channel=0)
+
+    def _view(self, par, off, count, dtype):
+        start = par * self.slot + off
+        return self.buf[start:start + count * dtype.itemsize].view(dtype)
+
+    def assignments(self, par):
+        """(argmin int32[world * rows], wmin float64[world * rows]) of this rank's buffer."""
+        total = self.world * self.rows
+        return (self._view(par, self.off_arg, total, torch.int32),
+                self._view(par, self.off_w, total, torch.float64))
+
+    def centroids(self, par):
+        return (self._view(par, self.off_prof, 136 * self.n_bins, torch.float64).view(self.n_bins, 136),
+                self._view(par, self.off_cov, self.n_samples * self.n_bins,
+                           torch.float64).view(self.n_bins, self.n_samples))
+
+    def push_assignments(self, ctx, par, d_argmin, d_wmin, stream=None):
+        """This rank's rows into everyone's gathered arrays (an all-gather by stores), on
+        ``stream`` (torch stream; default: the library's)."""
+        base = par * self.slot
+        st = stream.cuda_stream if stream is not None else None
+        ctx.push_to_peers(d_argmin.data_ptr(), 4 * self.rows,
+                          [p + base + self.off_arg + 4 * self.rank * self.rows for p in self.ptrs], st)
+        ctx.push_to_peers(d_wmin.data_ptr(), 8 * self.rows,
+                          [p + base + self.off_w + 8 * self.rank * self.rows for p in self.ptrs], st)
+
+    def push_centroids(self, ctx, par, cen_prof, cen_cov, stream=None):
+        """The source rank's bin tables into everyone's buffer (a broadcast by stores)."""
+        base = par * self.slot
+        st = stream.cuda_stream if stream is not None else None
+        ctx.push_to_peers(cen_prof.data_ptr(), cen_prof.numel() * 8,
+                          [p + base + self.off_prof for p in self.ptrs], st)
+        ctx.push_to_peers(cen_cov.data_ptr(), cen_cov.numel() * 8,
+                          [p + base + self.off_cov for p in self.ptrs], st)
+
+    def barrier(self, channel=0):
+        """All ranks meet on the CURRENT torch stream (everything pushed on it before has landed
+        everywhere when the barrier is passed)."""
+        self.handle.barrier(channel=channel)

@@ -111,6 +111,18 @@ def test_config2_full_size():
         ctx.step_resident()
         arg2, w2 = ctx.get_assignments()
         assert np.array_equal(arg2, arg) and np.array_equal(w2, w)
+        # the two halves of the step (multi-GPU callers put a broadcast between them), with SMs
+        # kept out of the persistent scan's grid, and every pair scored: same bits
+        ctx.set_reserved_sms(4)
+        ctx.set_prune(False)
+        ctx.step_featurise()
+        ctx.step_score()
+        ctx.set_prune(True)
+        ctx.set_reserved_sms(0)
+        arg4, w4 = ctx.get_assignments()
+        assert np.array_equal(arg4, arg) and np.array_equal(w4, w)
+        with pytest.raises(_lib.McgError):
+            ctx.set_reserved_sms(100000)
     finally:
         ctx.close()
 
