@@ -94,3 +94,32 @@ def test_pruned_argmin_is_the_argmin(n, B, S, spread):
     both = want_w != MAXW
     assert np.array_equal(w_p[pick][~both], want_w[~both])
     assert (np.abs(w_p[pick][both] - want_w[both]) / want_w[both]).max() <= 1e-9
+
+
+def test_candidate_list_overflow_falls_back_to_all_pairs():
+    """Every centroid is the same bin: every bin is a candidate of every contig, the list would
+    hold all pairs (more than its capacity, a quarter of them) and the device-side gate hands
+    the batch to prob_kernel.  First index of the minimum: bin 0."""
+    n, B, S = 2304, 96, 10
+    rng = np.random.default_rng(5)
+    one = rng.dirichlet(np.full(136, 40.0))
+    cen_prof = np.tile(one, (B, 1))
+    cen_cov = np.tile(rng.lognormal(np.log(20), 1.0, S), (B, 1))
+    prof = np.abs(one + rng.normal(0, 3e-4, (n, 136)))
+    prof /= prof.sum(axis=1, keepdims=True)
+    cov = np.maximum(cen_cov[0] * rng.normal(1.0, 0.1, (n, S)), 1e-4)
+    ctx = _lib.Context(0)
+    try:
+        ctx.set_profiles(prof)
+        ctx.load_coverage(cov)
+        arg_p, w_p, _ = ctx.score_centroids(cen_prof=cen_prof, cen_cov=cen_cov)
+        stats = ctx.prune_stats()
+        ctx.set_prune(False)
+        arg_f, w_f, _ = ctx.score_centroids(cen_prof=cen_prof, cen_cov=cen_cov)
+        assert ctx.prune_stats()["used"] is False
+    finally:
+        ctx.close()
+    assert stats["candidates"] == n * B and stats["candidates"] > stats["capacity"]
+    assert stats["used"] is False
+    assert np.array_equal(arg_p, arg_f) and np.array_equal(w_p, w_f)
+    assert (arg_p[w_p != MAXW] == 0).all() and (w_p != MAXW).mean() > 0.9
