@@ -577,7 +577,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "contigs_per_gpu": n, "bases_per_gpu": n_bases,
                    "samples": N_SAMPLES, "bins": N_BINS,
-                   "parallelism": ("row-sharded x%d, " % world) +
+                   "parallelism": "single GPU" if world == 1 else
+                                  ("row-sharded x%d, " % world) +
                                   ("bin tables and assignments exchanged by peer-memory stores "
                                    "(NVLink) + signal barrier" if peer is not None
                                    else "NCCL broadcast + all-gather"),
