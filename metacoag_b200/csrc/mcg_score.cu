@@ -796,7 +796,8 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
 // The arithmetic per pair is the same as pair_kernel<RULE_C, LOGSUM>.
 template <int DUMMY>
 __global__ void __launch_bounds__(kPairThreads, 3)
-dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc) {
+dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc,
+             unsigned long long *__restrict__ tilemin, long long n_btiles_all) {
     extern __shared__ __align__(16) double sm[];
     double *stage = sm;                                   // [2 stages][A, B][64][pitch]
     double *NA = stage + 4 * kChunkDoubles;
@@ -893,6 +894,7 @@ dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc
         }
         cp_async_commit();
         // d^2 = |u|^2 + |v|^2 - 2 u.v, clamped at 0; the scratch matrix is padded to whole tiles
+        unsigned long long rmin[2] = {~0ull, ~0ull};
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -906,8 +908,32 @@ dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc
                     v.y = v.y > 0.0 ? v.y : 0.0;
                     *reinterpret_cast<double2 *>(d2out + (a0 + row0 + 8 * i) * ldc + b0 + col0 +
                                                  8 * j) = v;
+                    if (tilemin) {
+                        // smallest d^2 of the row in this 64-bin tile, as ordered bits (d^2 >= 0;
+                        // a NaN counts as 0 so that its tile is never skipped); real bins only
+                        const long long c = b0 + col0 + 8 * j;
+                        const unsigned long long kx =
+                            v.x == v.x ? static_cast<unsigned long long>(__double_as_longlong(v.x)) : 0ull;
+                        const unsigned long long ky =
+                            v.y == v.y ? static_cast<unsigned long long>(__double_as_longlong(v.y)) : 0ull;
+                        if (c < B.n && kx < rmin[i]) rmin[i] = kx;
+                        if (c + 1 < B.n && ky < rmin[i]) rmin[i] = ky;
+                    }
                 }
             }
+        if (tilemin) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                unsigned long long k = rmin[i];
+#pragma unroll
+                for (int m = 1; m <= 2; m <<= 1) {   // the four lanes of a row
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, m);
+                    k = o < k ? o : k;
+                }
+                if (t == 0 && k != ~0ull && a0 + row0 + 8 * i < A.n)
+                    atomicMin(tilemin + (a0 + row0 + 8 * i) * n_btiles_all + bt, k);
+            }
+        }
         __syncthreads();
     }
     cp_async_wait<0>();
@@ -1172,7 +1198,8 @@ __global__ void bin_head_kernel(ScoreSide B, int S, int nq, long long ldh,
 
 __global__ void __launch_bounds__(256)
 bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
-             const double *__restrict__ head, long long ldh, CandList cl,
+             const double *__restrict__ head, long long ldh,
+             const unsigned long long *__restrict__ tilemin, CandList cl,
              int32_t *__restrict__ status) {
     __shared__ double ET[16];
     __shared__ double LT[128];
@@ -1188,12 +1215,31 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
     for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wid; r < A.n;
          r += n_warps) {
         const double *row = d2 + r * ldc;
-        // nearest centroid (first index on ties)
+        // dist2_kernel left the smallest d^2 of the row in every 64-bin tile (ordered bits):
+        // lane t holds tile t; tiles whose minimum is beyond a threshold are never read
+        const int nb = static_cast<int>(B.n);
+        const int nbt = (nb + 63) >> 6;
+        const unsigned long long tile_key = lane < nbt ? tilemin[r * nbt + lane] : ~0ull;
+        const double tile_d2 = __longlong_as_double(static_cast<long long>(
+            tile_key <= 0x7ff0000000000000ull ? tile_key : 0x7ff0000000000000ull));
+        // nearest centroid (first index on ties): the tile with the smallest minimum, then its bins
+        unsigned long long bk = tile_key;
+        int bt_near = lane;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, m);
+            const int ot = __shfl_xor_sync(0xffffffffu, bt_near, m);
+            if (ok < bk || (ok == bk && ot < bt_near)) { bk = ok; bt_near = ot; }
+        }
         double dm = INFINITY;
         int jm = 0;
-        for (int j = lane; j < B.n; j += 32) {
-            const double v = row[j];
-            if (v < dm) { dm = v; jm = j; }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 64 * bt_near + 32 * h + lane;
+            if (j < nb) {
+                const double v = row[j];
+                if (v < dm) { dm = v; jm = j; }
+            }
         }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
@@ -1262,7 +1308,9 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
             // LOWER bound of its weight from the distance and the head samples.
             double lb = INFINITY;
             int jb = 0;
+            const unsigned tiles2 = __ballot_sync(0xffffffffu, lane < nbt && !(tile_d2 > thr2));
             for (int sb = 0; sb < n_slabs; ++sb) {
+                if (!((tiles2 >> (sb >> 1)) & 1u)) continue;   // no bin of this tile is that near
                 const int j = 32 * sb + lane;
                 if (j < B.n) {
                     const double dd = row[j];
@@ -1295,8 +1343,11 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
             slack = w * (1.0 + 1e-9) * c_gauss.ln10 + sl + u_tail * (1.0 + 1e-9) - c_math.prune_c;
         // the candidates, in bin order; a NaN distance stays in
         int count = 0;
-        const int nb = static_cast<int>(B.n);
+        const unsigned tiles = __ballot_sync(0xffffffffu, lane < nbt && !(tile_d2 > thr2));
+        for (int sb = lane; sb < n_slabs; sb += 32) MASK[wid][sb] = 0u;
+        __syncwarp();
         for (int sb = 0; sb < n_slabs; ++sb) {
+            if (!((tiles >> (sb >> 1)) & 1u)) continue;   // every bin of this tile is beyond thr2
             const int j = 32 * sb + lane;
             const double dd = j < nb ? row[j] : INFINITY;
             bool keep = j < nb && !(dd > thr2);
@@ -1719,6 +1770,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
     }
     ctx->redo_valid = guard;
     CandList cl = {nullptr, 0, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *tilemin = nullptr;   // per (row, 64-bin tile) smallest d^2, from dist2_kernel
     ctx->cand_valid = false;
     if (use_cand) {
         // [total | pad] [start rows] [count rows] [pair cap] [w cap]
@@ -1737,7 +1789,9 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         ctx->cand_valid = true;
         ctx->cand_cap = cap;
         const int nq = S < kHeadSamples ? S : kHeadSamples;
-        MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(double) * 2 * nq * ldc));
+        // [head table 2 nq ldc doubles] [tile minima need_rows x b_tiles]
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(double) * (2 * nq * ldc + need_rows * b_tiles)));
+        tilemin = reinterpret_cast<unsigned long long *>(ctx->scratch[1].as<double>() + 2 * nq * ldc);
         bin_head_kernel<<<blocks_for(b.n * nq, 256), 256, 0, ctx->stream>>>(
             b, S, nq, ldc, ctx->scratch[1].as<double>());
         MCG_KERNEL_CHECK(ctx);
@@ -1757,7 +1811,11 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         if (gy < 1) gy = 1;
         dim3 grid(static_cast<unsigned>(a_tiles), static_cast<unsigned>(gy), 1);
         mcg_timer_begin(ctx, T_DIST);
-        dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc);
+        if (tilemin)   // 0x7f7f...: a finite number above every d^2
+            MCG_CUDA(ctx, cudaMemsetAsync(tilemin, 0x7f, sizeof(unsigned long long) * need_rows * b_tiles,
+                                          ctx->stream));
+        dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc, tilemin,
+                                                                       b_tiles);
         mcg_timer_end(ctx, T_DIST);
         MCG_KERNEL_CHECK(ctx);
         long long blocks = (ac.n + warps * kProbRows - 1) / (warps * kProbRows);
@@ -1770,7 +1828,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
             long long bb = (ac.n + 7) / 8;
             if (bb > 8LL * ctx->sm_count) bb = 8LL * ctx->sm_count;
             bound_kernel<<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
-                ac, b, S, d2, ldc, ctx->scratch[1].as<double>(), ldc, cl, d_status);
+                ac, b, S, d2, ldc, ctx->scratch[1].as<double>(), ldc, tilemin, cl, d_status);
             MCG_KERNEL_CHECK(ctx);
             const unsigned sb = static_cast<unsigned>(8 * ctx->sm_count);
             if (guard) {
