@@ -2,7 +2,10 @@
 """Measurements of the rows next to the hot path: the graph gate of
 match_contigs, the bin x bin merge matrix, the FASTA reader.  Prints one JSON object.
 
-    python tools/bench_aux.py            (needs a B200; the CPU side is timed in the same run)
+    python tests/bench_aux.py            (needs a B200; the CPU side is timed in the same run)
+
+Lives under tests/ because it checks every GPU number against the CPU oracle (test
+infrastructure, only tests may use it); pytest does not collect it.
 
 CPU comparisons restate what the reference does per call: one BFS per (source, target) pair
 (igraph get_shortest_paths, here a plain-Python BFS over the same CSR -- igraph itself is not
