@@ -123,3 +123,37 @@ def test_candidate_list_overflow_falls_back_to_all_pairs():
     assert stats["used"] is False
     assert np.array_equal(arg_p, arg_f) and np.array_equal(w_p, w_f)
     assert (arg_p[w_p != MAXW] == 0).all() and (w_p != MAXW).mean() > 0.9
+
+
+def test_pruned_equals_all_pairs_on_random_shapes():
+    """Seeded sweep over bin / sample counts around every boundary of the candidate path (one bin,
+    tile and slab edges of 32 / 64 bins, the 2048-bin limit of the candidate list, the S = 30 / 31
+    guard, more than one bin group): pruned == all pairs, bit for bit."""
+    rng = np.random.default_rng(2024)
+    shapes = [(1, 1), (2, 3), (31, 10), (32, 30), (33, 31), (63, 7), (64, 33), (65, 2), (129, 12),
+              (700, 40), (2048, 5), (2049, 5)]
+    ctx = _lib.Context(0)
+    try:
+        for B, S in shapes:
+            n = int(rng.integers(2048, 2600))
+            prof, cov, cen_prof, cen_cov = make_set(int(rng.integers(1 << 30)), n, max(B, 12), S,
+                                                    float(rng.choice([2e-4, 1e-3, 5e-3])))
+            cen_prof, cen_cov = cen_prof[:B], cen_cov[:B]
+            ctx.set_profiles(prof)
+            ctx.load_coverage(cov)
+            ctx.set_prune(True)
+            arg_p, w_p, _ = ctx.score_centroids(cen_prof=cen_prof, cen_cov=cen_cov)
+            used = ctx.prune_stats()
+            ctx.set_prune(False)
+            arg_f, w_f, _ = ctx.score_centroids(cen_prof=cen_prof, cen_cov=cen_cov)
+            assert np.array_equal(arg_p, arg_f), (B, S)
+            assert np.array_equal(w_p, w_f), (B, S)
+            assert (used["pairs"] == n * B) == (B <= 2048), (B, S, used)
+            # a gathered query list (rows through an index) takes the same path
+            q = rng.permutation(n)[:2100].astype(np.int64)
+            ctx.set_prune(True)
+            arg_q, w_q, _ = ctx.score_centroids(queries=q)
+            assert np.array_equal(arg_q, arg_f[q]) and np.array_equal(w_q, w_f[q]), (B, S)
+    finally:
+        ctx.set_prune(True)
+        ctx.close()
