@@ -18,6 +18,12 @@
 // in sample order per pair (the reference's running product decides the
 // prob_product > 0 branch through underflow), with log(c) and lgamma(c+1) hoisted per
 // (row, sample) by cov_terms_kernel.
+//
+// Rule C on large batches (every long contig against every bin): dist2_kernel (the d^2 matrix on
+// the FP64 tensor path, plus the smallest d^2 per row and 64-bin tile), then either prob_kernel
+// over every pair or, by default, the branch and bound: bound_kernel lists the bins that can
+// still beat the weight of the contig's nearest centroid, cand_score_kernel scores exactly
+// those, cand_argmin_kernel takes the first minimum (same bits as the all-pairs pass).
 #include "mcg_internal.cuh"
 
 namespace {
