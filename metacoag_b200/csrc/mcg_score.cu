@@ -1315,8 +1315,8 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
             double lb = INFINITY;
             int jb = 0;
             const unsigned tiles2 = __ballot_sync(0xffffffffu, lane < nbt && !(tile_d2 > thr2));
-            for (int sb = 0; sb < n_slabs; ++sb) {
-                if (!((tiles2 >> (sb >> 1)) & 1u)) continue;   // no bin of this tile is that near
+            for (unsigned tm = tiles2; tm; tm &= tm - 1)   // only the tiles with a bin that near
+            for (int sb = 2 * (__ffs(tm) - 1), h = 0; h < 2 && sb < n_slabs; ++h, ++sb) {
                 const int j = 32 * sb + lane;
                 if (j < B.n) {
                     const double dd = row[j];
@@ -1350,10 +1350,9 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
         // the candidates, in bin order; a NaN distance stays in
         int count = 0;
         const unsigned tiles = __ballot_sync(0xffffffffu, lane < nbt && !(tile_d2 > thr2));
-        for (int sb = lane; sb < n_slabs; sb += 32) MASK[wid][sb] = 0u;
         __syncwarp();
-        for (int sb = 0; sb < n_slabs; ++sb) {
-            if (!((tiles >> (sb >> 1)) & 1u)) continue;   // every bin of this tile is beyond thr2
+        for (unsigned tm = tiles; tm; tm &= tm - 1)   // the other tiles: every bin beyond thr2
+        for (int sb = 2 * (__ffs(tm) - 1), h = 0; h < 2 && sb < n_slabs; ++h, ++sb) {
             const int j = 32 * sb + lane;
             const double dd = j < nb ? row[j] : INFINITY;
             bool keep = j < nb && !(dd > thr2);
@@ -1386,7 +1385,8 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
         __syncwarp();
         if (base + count <= cl.cap) {
             int at = base;
-            for (int sb = 0; sb < n_slabs && at < base + count; ++sb) {
+            for (unsigned tm = tiles; tm && at < base + count; tm &= tm - 1)
+            for (int sb = 2 * (__ffs(tm) - 1), h = 0; h < 2 && sb < n_slabs; ++h, ++sb) {
                 const unsigned mask = MASK[wid][sb];
                 if (mask == 0u) continue;
                 if ((mask >> lane) & 1u)
