@@ -548,17 +548,26 @@ def main():
                                 "floor_wavefronts": 2.0 * n_bases / 32.0}
     kernels = [scan_roof]
     if kernel_ms.get("distance", 0.0) > 0.0:
-        # SURVEY 8d splits F_pair = 431 + 14 S into 136*3 for the distance and the rest
-        dist_flops = pairs * 136 * 3
-        prob_flops = pairs * (431 - 136 * 3 + 14 * N_SAMPLES)
+        # SURVEY 8d splits F_pair = 431 + 14 S into 136*3 for the distance and the rest.  The
+        # distance / probability timers hold ONE launch: with a chunked d^2 scratch (many rows x
+        # many bins) that is the last chunk, whose pair count the library reports.
+        chunk_pairs = float(prune_stats["pairs"]) if prune_stats.get("pairs") else pairs
+        dist_flops = chunk_pairs * 136 * 3
+        prob_flops = chunk_pairs * (431 - 136 * 3 + 14 * N_SAMPLES)
+        dmma = chunk_pairs * 136 * 2 / (kernel_ms_all["distance"] * 1e-3) / 1e12
         kernels.append(roof("dist2_kernel (DMMA distance GEMM)", "fp64", dist_flops,
-                            kernel_ms["distance"], fp64_peak, "TFLOP/s", fp64_src,
-                            algorithmic_flops=dist_flops,
-                            dmma_tflops=pairs * 136 * 2 / (kernel_ms["distance"] * 1e-3) / 1e12))
+                            kernel_ms_all["distance"], fp64_peak, "TFLOP/s", fp64_src,
+                            algorithmic_flops=dist_flops, pairs_per_launch=chunk_pairs,
+                            dmma_tflops=dmma, dmma_frac=dmma / fp64_peak,
+                            note="algorithmic flops count sub, mul, add per element (SURVEY 8d: "
+                                 "3 x 136 per pair); the kernel computes |u|^2 + |v|^2 - 2 u.v, "
+                                 "2 x 136 per pair on the FP64 tensor path, so `frac` can pass 1: "
+                                 "dmma_frac is the executed fraction of the unit's peak"))
         kernels.append(roof("prob_kernel (Poisson / Gaussian terms, argmin)", "fp64", prob_flops,
                             kernel_ms_all["probability"], fp64_peak, "TFLOP/s", fp64_src,
                             algorithmic_flops=prob_flops,
-                            gpairs_per_s=pairs / (kernel_ms_all["probability"] * 1e-3) / 1e9,
+                            pairs_per_launch=chunk_pairs,
+                            gpairs_per_s=chunk_pairs / (kernel_ms_all["probability"] * 1e-3) / 1e9,
                             note="every pair scored (mcg_set_prune 0); the product path prunes: "
                                  "%.4f ms" % kernel_ms["probability"]))
     score_roof = roof("rule-C scoring (distance + probability kernels)", "fp64", score_flops,
