@@ -1399,6 +1399,11 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
     }
 }
 
+__device__ __forceinline__ void ld_v4(double (&v)[4], const double *p) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
 // One thread per listed pair: the weight prob_kernel computes for it, operation for operation
 // (log_comp_prob_warp, excess sums in sample order, the e^-744 / e^-746 window, the GUARD
 // deferral); NaN marks a deferred pair.
@@ -1429,12 +1434,46 @@ cand_score_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2
             const double *ac_p = A.cov + arow * S, *al_p = A.logc + arow * S, *ag_p = A.lgam + arow * S;
             const double *bc_p = B.cov + brow * S, *bl_p = B.logc + brow * S, *bg_p = B.lgam + brow * S;
             double s1 = 0.0, s2 = 0.0;
+            if ((S & 3) == 0) {
+                // four samples per 32-byte load (sm_100: ld.global.v4.f64; rows of S % 4 == 0 are
+                // 32-byte aligned): one sector per lane and request instead of a quarter of one
+#pragma unroll 1
+                for (int h = 0; h < S; h += 4) {
+                    double ac[4], al[4], ag[4], bc[4], bl[4], bg[4];
+                    ld_v4(ac, ac_p + h); ld_v4(al, al_p + h); ld_v4(ag, ag_p + h);
+                    ld_v4(bc, bc_p + h); ld_v4(bl, bl_p + h); ld_v4(bg, bg_p + h);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        add_poisson_excess(s1, ac[u], -(ag[u] + c_math.log_floor), bc[u], bl[u]);
+                        add_poisson_excess(s2, bc[u], -(bg[u] + c_math.log_floor), ac[u], al[u]);
+                    }
+                }
+            } else if ((S & 1) == 0) {
+                // two samples per 16-byte load (rows of an even S are 16-byte aligned): half the
+                // L1TEX requests of the per-lane row walks that bound this kernel; same order
+                const double2 *ac2 = reinterpret_cast<const double2 *>(ac_p);
+                const double2 *al2 = reinterpret_cast<const double2 *>(al_p);
+                const double2 *ag2 = reinterpret_cast<const double2 *>(ag_p);
+                const double2 *bc2 = reinterpret_cast<const double2 *>(bc_p);
+                const double2 *bl2 = reinterpret_cast<const double2 *>(bl_p);
+                const double2 *bg2 = reinterpret_cast<const double2 *>(bg_p);
 #pragma unroll 2
-            for (int q = 0; q < S; ++q) {
-                const double ac = ac_p[q], al = al_p[q], am = -(ag_p[q] + c_math.log_floor);
-                const double bc = bc_p[q], bl = bl_p[q], bm = -(bg_p[q] + c_math.log_floor);
-                add_poisson_excess(s1, ac, am, bc, bl);
-                add_poisson_excess(s2, bc, bm, ac, al);
+                for (int h = 0; h < S / 2; ++h) {
+                    const double2 ac = ac2[h], al = al2[h], ag = ag2[h];
+                    const double2 bc = bc2[h], bl = bl2[h], bg = bg2[h];
+                    add_poisson_excess(s1, ac.x, -(ag.x + c_math.log_floor), bc.x, bl.x);
+                    add_poisson_excess(s2, bc.x, -(bg.x + c_math.log_floor), ac.x, al.x);
+                    add_poisson_excess(s1, ac.y, -(ag.y + c_math.log_floor), bc.y, bl.y);
+                    add_poisson_excess(s2, bc.y, -(bg.y + c_math.log_floor), ac.y, al.y);
+                }
+            } else {
+#pragma unroll 2
+                for (int q = 0; q < S; ++q) {
+                    const double ac = ac_p[q], al = al_p[q], am = -(ag_p[q] + c_math.log_floor);
+                    const double bc = bc_p[q], bl = bl_p[q], bm = -(bg_p[q] + c_math.log_floor);
+                    add_poisson_excess(s1, ac, am, bc, bl);
+                    add_poisson_excess(s2, bc, bm, ac, al);
+                }
             }
             const double pmin = fma(static_cast<double>(S), c_math.log_floor, s1 < s2 ? s1 : s2);
             tsum = log_pc + pmin;
