@@ -15,7 +15,8 @@
  *   - device memory is owned by the context (mcg_ctx) and freed by mcg_destroy;
  *   - every call returns 0 (MCG_OK) or a negative code; mcg_last_error() gives
  *     the message.  Nothing throws or exits across this boundary;
- *   - a context is bound to one CUDA device and is internally mutex-guarded
+ *   - a context is bound to one CUDA device (mcg_pool: one context per device of the box
+ *     behind one caller) and is internally mutex-guarded
  *     (label_prop_utils.assign_long is entered from several Python threads,
  *     metacoag:959-999, and ctypes drops the GIL);
  *   - there is no CPU fallback: without a CUDA device mcg_create() fails.
@@ -128,6 +129,11 @@ int mcg_prune_stats(mcg_ctx *ctx, int64_t stats[4]);
  * masked 512-bit tail; a level the CPU lacks falls back to the next lower one. */
 int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, int64_t n, uint8_t *packed,
                        int level);
+/* The same with `threads` host threads (<= 0: all hardware threads), contig ranges of equal
+ * bases each: the pass a FASTA reader runs once at parse time (feature_utils.py:131-138) so that
+ * every later upload of the contigs carries 2 bits per base instead of 8. */
+int mcg_pack_2bit_host_mt(const uint8_t *bases, const int64_t *offsets, int64_t n, uint8_t *packed,
+                          int threads);
 /* feature_utils.py:131-138, 182-186: the contigs are read with Bio.SeqIO.parse(path,
  * "fasta"), keeping record.id and str(record.seq).  These two host-only calls produce the same
  * names and sequences (BioPython's SimpleFastaParser rules: text before the first '>' skipped,
@@ -221,6 +227,34 @@ int mcg_bfs_candidates(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indic
                        int32_t *hit_node, int32_t *hit_bin, int32_t *hit_depth,
                        int32_t *n_hits);
 
+/* Rules A / B for LISTED (query, bin) items instead of the dense [queries, bins] matrix:
+ * label_prop_utils.py:54-86 (run_bfs_long) scores a candidate only against the bins its walk
+ * reached, a handful of the B bins.  item_query[i] = contig id, item_bin[i] = index into
+ * seg_offsets; weights[i] as mcg_score_members would give it (distance in the reference's
+ * difference form, matching_utils.py:28-29). */
+int mcg_score_member_items(mcg_ctx *ctx, const int64_t *item_query, const int32_t *item_bin,
+                           int64_t n_items, const int64_t *members, const int64_t *seg_offsets,
+                           int64_t nseg, int rule, double *weights);
+
+/* The label-propagation loops (label_prop_utils.py:230-303, 448-511) call run_bfs_long again for
+ * the contigs around EVERY accepted contig.  These calls keep the CSR assembly graph and the
+ * labels in the context, so that such a call moves its start nodes and its hits, not the graph:
+ *   mcg_graph_load   once per graph (labels start as all -1);
+ *   mcg_labels_load  all labels (labels[v] = bin of contig v or -1), once per stage;
+ *   mcg_labels_set   labels[ids[i]] = bins[i] -- one entry after every acceptance
+ *                    (label_prop_utils.py:270-271, 472-473);
+ *   mcg_bfs_resident the walks of mcg_bfs_candidates from `starts`, hits as flat lists: start i
+ *                    owns hits[hit_start[i] .. + hit_count[i]) as (labelled node, bin, depth)
+ *                    int32 triples in the reference's pop order.  *total = triples of all
+ *                    starts; when it exceeds hit_cap nothing else is valid and the caller
+ *                    comes back with a larger buffer. */
+int mcg_graph_load(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices, int64_t n_vertices);
+int mcg_labels_load(mcg_ctx *ctx, const int32_t *labels, int64_t n_vertices);
+int mcg_labels_set(mcg_ctx *ctx, const int64_t *ids, const int32_t *bins, int64_t n);
+int mcg_bfs_resident(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts, int depth_limit,
+                     int64_t *hit_start, int32_t *hit_count, int32_t *hits /* [hit_cap][3] */,
+                     int64_t hit_cap, int64_t *total);
+
 /* matching_utils.py:191-197 and :285-292 (graph gate of match_contigs): for every
  * (source, target) pair, len(assembly_graph.get_shortest_paths(source, to=target)[0]) -- the
  * number of vertices on a shortest path over the CSR assembly graph, 1 when source ==
@@ -280,6 +314,55 @@ int mcg_timings(mcg_ctx *ctx, float *ms /* [MCG_N_TIMERS] */, int64_t *launches)
  * double range (matching_utils.py:62-66 underflow).  This returns how many contigs the
  * last such call re-scored (0 when the path was not taken); it synchronises the stream. */
 int mcg_last_redo_count(mcg_ctx *ctx, int64_t *count);
+
+/* ---- device pool: the GPUs of one box behind one caller --------------- */
+/* The reference is ONE process (metacoag:191; its only fan-out is the thread pool around
+ * assign_long, metacoag:959-999), so a drop-in cannot ask for one process per GPU.  A pool owns
+ * one context and one host thread per device and splits every call itself:
+ *   - from raw bases (mcg_pool_tetramer_scan, mcg_pool_featurise_score): contiguous contig
+ *     ranges balanced by total bases, every device uploads / scans / scores its own rows and
+ *     writes its slice of the caller's arrays (mcg_pool_bounds: the ranges of the last call);
+ *   - staged features (mcg_pool_set_features + the scorers): tables replicated on every device,
+ *     QUERIES split evenly;
+ *   - label propagation: graph and labels replicated, start nodes split, hits concatenated in
+ *     start order.
+ * Arguments, results and errors are those of the per-context calls of the same name; results do
+ * not depend on the number of devices (bit for bit).  devices = NULL: all devices, or the first
+ * MCG_DEVICES of them.  One pool call runs at a time (internally serialised). */
+typedef struct mcg_pool mcg_pool;
+mcg_pool *mcg_pool_create(const int *devices, int n);   /* NULL on failure */
+void mcg_pool_destroy(mcg_pool *pool);
+int mcg_pool_size(const mcg_pool *pool);
+mcg_ctx *mcg_pool_ctx(mcg_pool *pool, int i);           /* context of the i-th device */
+const char *mcg_pool_last_error(const mcg_pool *pool);
+int mcg_pool_bounds(mcg_pool *pool, int64_t *bounds /* [size + 1] */);
+int mcg_pool_tetramer_scan(mcg_pool *pool, const uint8_t *bases, const int64_t *offsets, int64_t n,
+                           int encoding, uint32_t *counts, double *freqs);
+int mcg_pool_featurise_score(mcg_pool *pool, const uint8_t *bases, const int64_t *offsets,
+                             int64_t n, int encoding, const double *cov, int n_samples,
+                             const double *cen_prof, const double *cen_cov, int64_t n_bins,
+                             int32_t *argmin, double *wmin);
+int mcg_pool_set_features(mcg_pool *pool, const double *prof /* [n_prof,136] or NULL */,
+                          int64_t n_prof, const double *cov /* [n_cov,S] or NULL */, int64_t n_cov,
+                          int n_samples);
+int mcg_pool_bin_profiles(mcg_pool *pool, const int64_t *members, const int64_t *seg_offsets,
+                          int64_t nseg, double *cen_prof, double *cen_cov);
+int mcg_pool_score_centroids(mcg_pool *pool, const int64_t *queries, int64_t nq,
+                             const double *cen_prof, const double *cen_cov, int64_t n_bins,
+                             double *weights, int32_t *argmin, double *wmin);
+int mcg_pool_score_members(mcg_pool *pool, const int64_t *queries, int64_t nq,
+                           const int64_t *members, const int64_t *seg_offsets, int64_t nseg,
+                           int rule, double *weights);
+int mcg_pool_score_member_items(mcg_pool *pool, const int64_t *item_query, const int32_t *item_bin,
+                                int64_t n_items, const int64_t *members, const int64_t *seg_offsets,
+                                int64_t nseg, int rule, double *weights);
+int mcg_pool_graph_load(mcg_pool *pool, const int64_t *indptr, const int32_t *indices,
+                        int64_t n_vertices);
+int mcg_pool_labels_load(mcg_pool *pool, const int32_t *labels, int64_t n_vertices);
+int mcg_pool_labels_set(mcg_pool *pool, const int64_t *ids, const int32_t *bins, int64_t n);
+int mcg_pool_bfs(mcg_pool *pool, const int64_t *starts, int64_t n_starts, int depth_limit,
+                 int64_t *hit_start, int32_t *hit_count, int32_t *hits, int64_t hit_cap,
+                 int64_t *total);
 
 /* ---- synthetic workloads (bench / tests) ------------------ */
 /* Fill a device-generated ASCII contig set: per-genome first-order Markov bases,

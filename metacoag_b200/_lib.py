@@ -80,6 +80,30 @@ SIGNATURES = {
     "mcg_fasta_index": (_int, [_c.c_char_p, _vp, _vp, _vp]),
     "mcg_fasta_load": (_int, [_c.c_char_p, _vp, _vp, _vp, _vp, _i64, _i64, _i64]),
     "mcg_write_bin_fastas": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _c.c_int32]),
+    "mcg_pack_2bit_host_mt": (_int, [_vp, _vp, _i64, _vp, _int]),
+    "mcg_score_member_items": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp]),
+    "mcg_graph_load": (_int, [_vp, _vp, _vp, _i64]),
+    "mcg_labels_load": (_int, [_vp, _vp, _i64]),
+    "mcg_labels_set": (_int, [_vp, _vp, _vp, _i64]),
+    "mcg_bfs_resident": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _i64, _vp]),
+    "mcg_pool_create": (_vp, [_vp, _int]),
+    "mcg_pool_destroy": (None, [_vp]),
+    "mcg_pool_size": (_int, [_vp]),
+    "mcg_pool_ctx": (_vp, [_vp, _int]),
+    "mcg_pool_last_error": (_c.c_char_p, [_vp]),
+    "mcg_pool_bounds": (_int, [_vp, _vp]),
+    "mcg_pool_tetramer_scan": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
+    "mcg_pool_featurise_score": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _i64,
+                                        _vp, _vp]),
+    "mcg_pool_set_features": (_int, [_vp, _vp, _i64, _vp, _i64, _int]),
+    "mcg_pool_bin_profiles": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "mcg_pool_score_centroids": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mcg_pool_score_members": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _vp]),
+    "mcg_pool_score_member_items": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp]),
+    "mcg_pool_graph_load": (_int, [_vp, _vp, _vp, _i64]),
+    "mcg_pool_labels_load": (_int, [_vp, _vp, _i64]),
+    "mcg_pool_labels_set": (_int, [_vp, _vp, _vp, _i64]),
+    "mcg_pool_bfs": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _i64, _vp]),
 }
 
 
@@ -122,14 +146,31 @@ def _arr(a, dtype, shape=None):
     return a
 
 
-def pack_2bit_host(bases, offsets, level=-1):
-    """ASCII contigs -> MCG_ENC_2BIT bytes with the library's host packer (no device)."""
+def packed_nbytes(offsets):
+    """Bytes of the MCG_ENC_2BIT store of contigs with these offsets (16 per 64 bases, every
+    contig padded to a multiple of 64)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    return int(np.sum(16 * ((np.diff(offsets) + 63) // 64)))
+
+
+def pack_2bit_host(bases, offsets, level=-1, threads=None, pinned=False):
+    """ASCII contigs -> MCG_ENC_2BIT bytes with the library's host packer (no device).
+    ``threads`` (None: one thread, SIMD variant ``level``; 0: all hardware threads) selects the
+    parallel packer a FASTA reader runs at parse time."""
     bases = _arr(bases, np.uint8)
     offsets = _arr(offsets, np.int64)
     n = offsets.shape[0] - 1
-    nbytes = int(np.sum(16 * ((np.diff(offsets) + 63) // 64)))
-    out = np.zeros(nbytes, dtype=np.uint8)
-    rc = load_library().mcg_pack_2bit_host(_ptr(bases), _ptr(offsets), n, _ptr(out), int(level))
+    nbytes = packed_nbytes(offsets)
+    if pinned and nbytes:
+        out = pinned_empty(nbytes)
+        out[:] = 0
+    else:
+        out = np.zeros(nbytes, dtype=np.uint8)
+    lib = load_library()
+    if threads is None:
+        rc = lib.mcg_pack_2bit_host(_ptr(bases), _ptr(offsets), n, _ptr(out), int(level))
+    else:
+        rc = lib.mcg_pack_2bit_host_mt(_ptr(bases), _ptr(offsets), n, _ptr(out), int(threads))
     if rc != OK:
         raise McgError(rc, "mcg_pack_2bit_host failed")
     return out
@@ -218,10 +259,18 @@ class Context:
         except Exception:
             pass
 
+    _RENAMED = {"bfs": "mcg_bfs_resident"}
+
+    def _fn(self, name):
+        return getattr(self.lib, self._RENAMED.get(name, "mcg_" + name))
+
+    def _last_error(self):
+        return (self.lib.mcg_last_error(self.handle) or b"").decode()
+
     def _check(self, rc):
         if rc == OK:
             return
-        msg = (self.lib.mcg_last_error(self.handle) or b"").decode()
+        msg = self._last_error()
         if rc == ERR_DOMAIN:
             # what the reference raises at matching_utils.py:39 when both Gaussians underflow
             raise ZeroDivisionError("float division by zero")
@@ -296,7 +345,7 @@ class Context:
         n = offsets.shape[0] - 1
         counts = np.zeros((n, NPROF), dtype=np.uint32) if want_counts else None
         freqs = np.zeros((n, NPROF), dtype=np.float64) if want_freqs else None
-        self._check(self.lib.mcg_tetramer_scan(self.handle, _ptr(bases), _ptr(offsets), n,
+        self._check(self._fn("tetramer_scan")(self.handle, _ptr(bases), _ptr(offsets), n,
                                                encoding, _ptr(counts), _ptr(freqs)))
         self.n_contigs = n
         return counts, freqs
@@ -348,7 +397,7 @@ class Context:
         nseg = seg_offsets.shape[0] - 1
         cen_prof = np.zeros((nseg, NPROF))
         cen_cov = np.zeros((nseg, self.n_samples))
-        self._check(self.lib.mcg_bin_profiles(self.handle, _ptr(members), _ptr(seg_offsets), nseg,
+        self._check(self._fn("bin_profiles")(self.handle, _ptr(members), _ptr(seg_offsets), nseg,
                                               _ptr(cen_prof), _ptr(cen_cov)))
         self.n_bins = nseg
         return cen_prof, cen_cov
@@ -418,7 +467,7 @@ class Context:
         weights = np.zeros((nq, n_bins)) if want_weights else None
         argmin = np.zeros(nq, dtype=np.int32)
         wmin = np.zeros(nq)
-        self._check(self.lib.mcg_score_centroids(self.handle, _ptr(queries), nq, _ptr(cen_prof),
+        self._check(self._fn("score_centroids")(self.handle, _ptr(queries), nq, _ptr(cen_prof),
                                                  _ptr(cen_cov), n_bins, _ptr(weights),
                                                  _ptr(argmin), _ptr(wmin)))
         return argmin, wmin, weights
@@ -429,7 +478,7 @@ class Context:
         seg_offsets = _arr(seg_offsets, np.int64)
         nseg = seg_offsets.shape[0] - 1
         weights = np.zeros((queries.shape[0], nseg))
-        self._check(self.lib.mcg_score_members(self.handle, _ptr(queries), queries.shape[0],
+        self._check(self._fn("score_members")(self.handle, _ptr(queries), queries.shape[0],
                                                _ptr(members), _ptr(seg_offsets), nseg, int(rule),
                                                _ptr(weights)))
         return weights
@@ -475,6 +524,54 @@ class Context:
                                                       indptr.shape[0] - 1, _ptr(labels)))
         return labels
 
+    def score_member_items(self, item_query, item_bin, members, seg_offsets, rule):
+        """Rules A / B for listed (contig, bin index) items: float64[n_items]."""
+        item_query = _arr(item_query, np.int64)
+        item_bin = _arr(item_bin, np.int32)
+        members = _arr(members, np.int64)
+        seg_offsets = _arr(seg_offsets, np.int64)
+        weights = np.zeros(item_query.shape[0])
+        self._check(self._fn("score_member_items")(
+            self.handle, _ptr(item_query), _ptr(item_bin), item_query.shape[0], _ptr(members),
+            _ptr(seg_offsets), seg_offsets.shape[0] - 1, int(rule), _ptr(weights)))
+        return weights
+
+    # -- resident assembly graph (label propagation) ---------------------------------------------
+    def graph_load(self, indptr, indices):
+        indptr = _arr(indptr, np.int64)
+        indices = _arr(indices, np.int32)
+        self._check(self._fn("graph_load")(self.handle, _ptr(indptr), _ptr(indices),
+                                           indptr.shape[0] - 1))
+        self.n_vertices = indptr.shape[0] - 1
+
+    def labels_load(self, labels):
+        labels = _arr(labels, np.int32)
+        self._check(self._fn("labels_load")(self.handle, _ptr(labels), labels.shape[0]))
+
+    def labels_set(self, ids, bins):
+        ids = _arr(ids, np.int64).reshape(-1)
+        bins = _arr(bins, np.int32).reshape(-1)
+        self._check(self._fn("labels_set")(self.handle, _ptr(ids), _ptr(bins), ids.shape[0]))
+
+    def bfs_resident(self, starts, depth_limit):
+        """Walks from ``starts`` over the resident graph: (hit_start int64[n], hit_count
+        int32[n], hits int32[total, 3] = (labelled node, bin, depth)), hits of a start
+        contiguous and in the reference's pop order."""
+        starts = _arr(starts, np.int64).reshape(-1)
+        ns = starts.shape[0]
+        hit_start = np.zeros(ns, dtype=np.int64)
+        hit_count = np.zeros(ns, dtype=np.int32)
+        cap = 4 * ns + 256
+        total = _c.c_int64(0)
+        while True:
+            hits = np.zeros((cap, 3), dtype=np.int32)
+            self._check(self._fn("bfs")(
+                self.handle, _ptr(starts), ns, int(depth_limit), _ptr(hit_start), _ptr(hit_count),
+                _ptr(hits), cap, _c.byref(total)))
+            if total.value <= cap:
+                return hit_start, hit_count, hits[:total.value]
+            cap = int(total.value)
+
     # -- fused / resident ---------------------------------------------------------------------
     def featurise_score(self, bases, offsets, cov, cen_prof, cen_cov, encoding=ENC_ASCII,
                         argmin=None, wmin=None):
@@ -487,7 +584,7 @@ class Context:
             argmin = np.zeros(n, dtype=np.int32)
         if wmin is None:
             wmin = np.zeros(n)
-        self._check(self.lib.mcg_featurise_score(
+        self._check(self._fn("featurise_score")(
             self.handle, _ptr(bases), _ptr(offsets), n, encoding, _ptr(cov), cov.shape[1],
             _ptr(cen_prof), _ptr(cen_cov), cen_prof.shape[0], _ptr(argmin), _ptr(wmin)))
         self.n_contigs, self.n_samples, self.n_bins = n, cov.shape[1], cen_prof.shape[0]
@@ -584,3 +681,110 @@ def default_context(device=None):
             ctx = Context(device)
             _default[device] = ctx
         return ctx
+
+
+class Pool(Context):
+    """One ``mcg_pool``: every GPU of the box (or the first ``MCG_DEVICES``) behind one caller.
+    The pooled calls have the signatures of the per-context ones (include/mcg_b200.h); every
+    other method runs on the first device's context."""
+
+    _POOLED = {"tetramer_scan", "featurise_score", "bin_profiles", "score_centroids",
+               "score_members", "score_member_items", "graph_load", "labels_load", "labels_set",
+               "bfs"}
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        if devices is None:
+            self.pool = self.lib.mcg_pool_create(None, 0)
+        else:
+            arr = (_c.c_int * len(devices))(*[int(d) for d in devices])
+            self.pool = self.lib.mcg_pool_create(arr, len(devices))
+        if not self.pool:
+            msg = self.lib.mcg_last_error(None)
+            raise McgError(ERR_CUDA, (msg or b"mcg_pool_create failed").decode())
+        self.size = int(self.lib.mcg_pool_size(self.pool))
+        self.first = self.lib.mcg_pool_ctx(self.pool, 0)
+        self.handle = self.first
+        self.device = 0
+        self.n_contigs = self.n_samples = self.n_bins = 0
+
+    def close(self):
+        if getattr(self, "pool", None):
+            self.lib.mcg_pool_destroy(self.pool)
+            self.pool = None
+            self.handle = None
+
+    def contexts(self):
+        """Borrowed per-device handles (valid while the pool lives)."""
+        out = []
+        for i in range(self.size):
+            c = Context.__new__(Context)
+            c.lib, c.handle, c.device = self.lib, self.lib.mcg_pool_ctx(self.pool, i), i
+            c.n_contigs = c.n_samples = c.n_bins = 0
+            c.close = lambda: None
+            out.append(c)
+        return out
+
+    def _fn(self, name):
+        if name in self._POOLED:
+            fn = getattr(self.lib, "mcg_pool_" + name)
+            pool = self.pool
+
+            def call(_handle, *args):
+                self._pooled_call = True
+                return fn(pool, *args)
+            return call
+        return Context._fn(self, name)
+
+    def _last_error(self):
+        if getattr(self, "_pooled_call", False):
+            self._pooled_call = False
+            return (self.lib.mcg_pool_last_error(self.pool) or b"").decode()
+        return Context._last_error(self)
+
+    def bounds(self):
+        out = np.zeros(self.size + 1, dtype=np.int64)
+        self.lib.mcg_pool_bounds(self.pool, _ptr(out))
+        return out
+
+    def set_features(self, prof=None, cov=None):
+        """Feature tables of every contig, replicated on every device."""
+        if prof is not None:
+            prof = _arr(prof, np.float64)
+            if prof.ndim != 2 or prof.shape[1] != NPROF:
+                raise ValueError("profiles must be [n,136]")
+            self.n_contigs = prof.shape[0]
+        if cov is not None:
+            cov = _arr(cov, np.float64)
+            if cov.ndim != 2:
+                raise ValueError("coverage must be [n,S]")
+            self.n_samples = cov.shape[1]
+            self._cov_rows = cov.shape[0]
+        self._pooled_call = True
+        self._check(self.lib.mcg_pool_set_features(
+            self.pool, _ptr(prof), 0 if prof is None else prof.shape[0], _ptr(cov),
+            0 if cov is None else cov.shape[0], 0 if cov is None else cov.shape[1]))
+
+    def set_profiles(self, prof):
+        self.set_features(prof=prof)
+
+    def load_coverage(self, cov):
+        self.set_features(cov=cov)
+
+
+_pool = None
+
+
+def default_pool():
+    """Process-wide device pool of the drop-in modules.  Under torchrun (LOCAL_RANK set) every
+    process owns its one device; a single process takes every device (MCG_DEVICES limits)."""
+    global _pool
+    with _default_lock:
+        if _pool is None:
+            if "LOCAL_RANK" in os.environ and "MCG_DEVICES" not in os.environ:
+                _pool = Pool([int(os.environ.get("MCG_DEVICE", os.environ["LOCAL_RANK"]))])
+            elif "MCG_DEVICE" in os.environ:
+                _pool = Pool([int(os.environ["MCG_DEVICE"])])
+            else:
+                _pool = Pool()
+        return _pool

@@ -173,12 +173,15 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->packed, &ctx->meta, &ctx->seg_contig, &ctx->ascii, &ctx->offsets,
                       &ctx->tile_counter, &ctx->counts, &ctx->prof, &ctx->cov, &ctx->logc,
                       &ctx->lgam, &ctx->cen_prof, &ctx->cen_cov, &ctx->cen_logc, &ctx->cen_lgam,
-                      &ctx->argmin, &ctx->wmin, &ctx->status, &ctx->prof_norm, &ctx->cen_norm};
+                      &ctx->argmin, &ctx->wmin, &ctx->status, &ctx->prof_norm, &ctx->cen_norm,
+                      &ctx->g_indptr, &ctx->g_indices, &ctx->g_labels, &ctx->g_work, &ctx->g_block,
+                      &ctx->g_starts, &ctx->g_patch};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->scratch)
         if (b.p) cudaFree(b.p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->g_pinned) cudaFreeHost(ctx->g_pinned);
     if (ctx->pinned_pack) cudaFreeHost(ctx->pinned_pack);
     if (ctx->copy2_done) cudaEventDestroy(ctx->copy2_done);
     if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
@@ -594,8 +597,46 @@ static int load_contigs_locked(mcg_ctx *ctx, const uint8_t *bases, const int64_t
             } else {
                 MCG_TRY(upload_ascii(ctx, bases, offsets, n, meta, n_words));
             }
+        } else if (wave_factory && n_words > 0) {
+            // 2-bit input (packed at parse time): the copy is cut at contig boundaries into
+            // ~16 MB runs on the copy stream, and every run is scanned and scored behind its
+            // own event while the next one is on the wire
+            ctx->n_contigs = n;
+            ctx->n_words = n_words;
+            ctx->n_seg = n_seg;
+            ctx->n_bases = n_bases;
+            const WaveFn wave = (*wave_factory)(meta, n_seg);
+            const int64_t run_words = std::max<int64_t>((4 << 20), n_words / 12);
+            MCG_CUDA(ctx, cudaEventRecord(ctx->copy_start, ctx->stream));
+            MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_start, 0));
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(bases);
+            int slot = 0;
+            for (int64_t c0 = 0; c0 < n;) {
+                const int64_t w0 = meta[c0].pk_word;
+                // first contig whose words start at or beyond w0 + run_words
+                int64_t lo = c0 + 1, hi = n;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) / 2;
+                    if (meta[mid].pk_word - w0 < run_words) lo = mid + 1; else hi = mid;
+                }
+                const int64_t c1 = lo;
+                const int64_t w1 = c1 < n ? meta[c1].pk_word : n_words;
+                if (w1 > w0)
+                    MCG_CUDA(ctx, cudaMemcpyAsync(ctx->packed.as<uint32_t>() + w0, src + w0,
+                                                  sizeof(uint32_t) * (w1 - w0), cudaMemcpyHostToDevice,
+                                                  ctx->copy_stream));
+                MCG_CUDA(ctx, cudaEventRecord(ctx->copy_ev[slot], ctx->copy_stream));
+                MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[slot], 0));
+                slot = (slot + 1) & 7;
+                MCG_TRY(wave(c0, c1));
+                c0 = c1;
+            }
+            ctx->ingest_stats[0] = static_cast<int64_t>(sizeof(uint32_t)) * n_words;
+            ctx->ingest_stats[1] = ctx->ingest_stats[2] = ctx->ingest_stats[3] = 0;
         } else {
             MCG_TRY(h2d(ctx, ctx->packed.p, bases, sizeof(uint32_t) * n_words));
+            ctx->ingest_stats[0] = static_cast<int64_t>(sizeof(uint32_t)) * n_words;
+            ctx->ingest_stats[1] = ctx->ingest_stats[2] = ctx->ingest_stats[3] = 0;
         }
     }
     // the pinned meta block must not be overwritten before the copy has left
@@ -1106,6 +1147,205 @@ extern "C" int mcg_bfs_candidates(mcg_ctx *ctx, const int64_t *indptr, const int
     return MCG_OK;
 }
 
+// ---- resident assembly graph: label propagation at scale ------------------------------------------
+extern "C" int mcg_graph_load(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
+                              int64_t n_vertices) {
+    MCG_ENTER(ctx);
+    if (n_vertices <= 0 || !indptr) return mcg_fail(ctx, MCG_ERR_ARG, "bad graph arguments");
+    if (n_vertices > 0x7ffffff0LL) return mcg_fail(ctx, MCG_ERR_ARG, "too many vertices");
+    const int64_t n_edges = indptr[n_vertices];
+    if (indptr[0] != 0 || n_edges < 0 || (n_edges > 0 && !indices))
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad CSR arrays");
+    for (int64_t v = 0; v < n_vertices; ++v)
+        if (indptr[v + 1] < indptr[v]) return mcg_fail(ctx, MCG_ERR_ARG, "indptr must not decrease");
+    for (int64_t e = 0; e < n_edges; ++e)
+        if (indices[e] < 0 || indices[e] >= n_vertices)
+            return mcg_fail(ctx, MCG_ERR_ARG, "edge endpoint %d out of range", indices[e]);
+    MCG_TRY(mcg_reserve(ctx, ctx->g_indptr, sizeof(int64_t) * (n_vertices + 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->g_indices, sizeof(int32_t) * std::max<int64_t>(n_edges, 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->g_labels, sizeof(int32_t) * n_vertices));
+    MCG_TRY(h2d(ctx, ctx->g_indptr.p, indptr, sizeof(int64_t) * (n_vertices + 1)));
+    MCG_TRY(h2d(ctx, ctx->g_indices.p, indices, sizeof(int32_t) * n_edges));
+    MCG_CUDA(ctx, cudaMemsetAsync(ctx->g_labels.p, 0xff, sizeof(int32_t) * n_vertices, ctx->stream));
+    MCG_TRY(sync(ctx));
+    ctx->g_vertices = n_vertices;
+    ctx->g_edges = n_edges;
+    return MCG_OK;
+}
+
+extern "C" int mcg_labels_load(mcg_ctx *ctx, const int32_t *labels, int64_t n_vertices) {
+    MCG_ENTER(ctx);
+    if (ctx->g_vertices == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no graph resident (mcg_graph_load)");
+    if (!labels || n_vertices != ctx->g_vertices)
+        return mcg_fail(ctx, MCG_ERR_ARG, "labels must cover the %lld vertices of the resident graph",
+                        (long long)ctx->g_vertices);
+    MCG_TRY(h2d(ctx, ctx->g_labels.p, labels, sizeof(int32_t) * n_vertices));
+    return sync(ctx);
+}
+
+struct LabelPatch {
+    long long id[16];
+    int bin[16];
+    int n;
+};
+static __global__ void labels_patch_kernel(int32_t *labels, LabelPatch p) {
+    if (threadIdx.x < p.n) labels[p.id[threadIdx.x]] = p.bin[threadIdx.x];
+}
+
+extern "C" int mcg_labels_set(mcg_ctx *ctx, const int64_t *ids, const int32_t *bins, int64_t n) {
+    MCG_ENTER(ctx);
+    if (ctx->g_vertices == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no graph resident (mcg_graph_load)");
+    if (n < 0 || (n > 0 && (!ids || !bins))) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    MCG_TRY(check_ids(ctx, ids, n, ctx->g_vertices, "ids"));
+    if (n == 0) return MCG_OK;
+    if (n <= 16) {
+        // the usual call (one accepted contig): the patch travels in the kernel arguments
+        LabelPatch p;
+        p.n = static_cast<int>(n);
+        for (int i = 0; i < p.n; ++i) { p.id[i] = ids[i]; p.bin[i] = bins[i]; }
+        labels_patch_kernel<<<1, 32, 0, ctx->stream>>>(ctx->g_labels.as<int32_t>(), p);
+        MCG_KERNEL_CHECK(ctx);
+        return MCG_OK;
+    }
+    MCG_TRY(mcg_reserve(ctx, ctx->g_patch, 12 * static_cast<size_t>(n)));
+    int64_t *d_ids = ctx->g_patch.as<int64_t>();
+    int32_t *d_bins = reinterpret_cast<int32_t *>(d_ids + n);
+    MCG_TRY(h2d(ctx, d_ids, ids, sizeof(int64_t) * n));
+    MCG_TRY(h2d(ctx, d_bins, bins, sizeof(int32_t) * n));
+    MCG_TRY(mcg_k_labels_set(ctx, ctx->g_labels.as<int32_t>(), d_ids, d_bins, n));
+    return sync(ctx);   // ids / bins are the caller's again
+}
+
+extern "C" int mcg_bfs_resident(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts,
+                                int depth_limit, int64_t *hit_start, int32_t *hit_count,
+                                int32_t *hits, int64_t hit_cap, int64_t *total) {
+    MCG_ENTER(ctx);
+    if (ctx->g_vertices == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no graph resident (mcg_graph_load)");
+    if (n_starts < 0 || hit_cap < 0 || !total || (n_starts > 0 && (!starts || !hit_start || !hit_count)) ||
+        (hit_cap > 0 && !hits))
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    *total = 0;
+    if (n_starts == 0) return MCG_OK;
+    if (n_starts > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many start nodes");
+    MCG_TRY(check_ids(ctx, starts, n_starts, ctx->g_vertices, "starts"));
+    const int64_t n8 = (n_starts + 1) / 2 * 2;
+    const size_t head_bytes = 16 + 8 * static_cast<size_t>(n_starts) + 8 * static_cast<size_t>(n8);
+    MCG_TRY(mcg_reserve(ctx, ctx->g_block, head_bytes + 12 * static_cast<size_t>(hit_cap)));
+    MCG_TRY(mcg_reserve(ctx, ctx->g_starts, sizeof(int64_t) * n_starts));
+    MCG_TRY(mcg_reserve(ctx, ctx->g_work, mcg_walk_work_bytes(n_starts)));
+    char *blk = ctx->g_block.as<char>();
+    MCG_TRY(h2d(ctx, ctx->g_starts.p, starts, sizeof(int64_t) * n_starts));
+    {
+        TimerScope t(ctx, T_OTHER);
+        MCG_TRY(mcg_k_walks(ctx, ctx->g_indptr.as<int64_t>(), ctx->g_indices.as<int32_t>(),
+                            ctx->g_labels.as<int32_t>(), ctx->g_starts.as<int64_t>(), n_starts,
+                            depth_limit, ctx->g_work.as<int32_t>(), blk, hit_cap));
+    }
+    // Small calls (the few contigs around one accepted contig) come back in ONE copy and one
+    // synchronisation: header, ranges and the first hits speculatively, through pinned memory.
+    struct Head { long long total; int n_redo, n_failed; } head;
+    const bool small = n_starts <= 4096;
+    const int64_t spec_hits = small ? std::min<int64_t>(hit_cap, 4 * n_starts + 256) : 0;
+    const size_t spec_bytes = head_bytes + 12 * static_cast<size_t>(spec_hits);
+    if (small) {
+        if (spec_bytes > ctx->g_pinned_cap) {
+            if (ctx->g_pinned) cudaFreeHost(ctx->g_pinned);
+            ctx->g_pinned = nullptr;
+            ctx->g_pinned_cap = 0;
+            const size_t want = std::max<size_t>(spec_bytes, 1 << 16);
+            if (cudaMallocHost(&ctx->g_pinned, want) != cudaSuccess)
+                return mcg_fail(ctx, MCG_ERR_NOMEM, "cudaMallocHost(%zu) failed", want);
+            ctx->g_pinned_cap = want;
+        }
+        MCG_TRY(d2h(ctx, ctx->g_pinned, blk, spec_bytes));
+        MCG_TRY(sync(ctx));
+        memcpy(&head, ctx->g_pinned, sizeof head);
+    } else {
+        MCG_TRY(d2h(ctx, &head, blk, sizeof head));
+        MCG_TRY(sync(ctx));
+    }
+    bool redone = false;
+    if (head.n_redo > 0) {
+        redone = true;
+        for (int64_t stride = 4096;; stride *= 4) {
+            const size_t bytes = sizeof(int32_t) * static_cast<size_t>(stride) * head.n_redo;
+            if (bytes > (size_t(8) << 30))
+                return mcg_fail(ctx, MCG_ERR_NOMEM, "BFS work buffer would exceed 8 GiB");
+            MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], bytes));
+            MCG_TRY(mcg_k_walks_redo(ctx, ctx->g_indptr.as<int64_t>(), ctx->g_indices.as<int32_t>(),
+                                     ctx->g_labels.as<int32_t>(), ctx->g_starts.as<int64_t>(),
+                                     n_starts, head.n_redo, depth_limit,
+                                     ctx->scratch[0].as<int32_t>(), stride, blk, hit_cap));
+            Head again;
+            MCG_TRY(d2h(ctx, &again, blk, sizeof again));
+            MCG_TRY(sync(ctx));
+            head.total = again.total;
+            if (again.n_failed == 0) break;
+        }
+    }
+    *total = head.total;
+    if (head.total > hit_cap) return MCG_OK;   // the caller comes back with a larger buffer
+    if (small && !redone && head.total <= spec_hits) {
+        const char *src = static_cast<const char *>(ctx->g_pinned);
+        memcpy(hit_start, src + 16, sizeof(int64_t) * n_starts);
+        memcpy(hit_count, src + 16 + 8 * n_starts, sizeof(int32_t) * n_starts);
+        if (head.total) memcpy(hits, src + head_bytes, 12 * static_cast<size_t>(head.total));
+        return MCG_OK;
+    }
+    TimerScope t(ctx, T_D2H);
+    MCG_TRY(d2h(ctx, hit_start, blk + 16, sizeof(int64_t) * n_starts));
+    MCG_TRY(d2h(ctx, hit_count, blk + 16 + 8 * n_starts, sizeof(int32_t) * n_starts));
+    MCG_TRY(d2h(ctx, hits, blk + head_bytes, 12 * static_cast<size_t>(head.total)));
+    return sync(ctx);
+}
+
+// Rules A / B for listed (query, bin) items: label_prop_utils.py:54-86 scores a candidate only
+// against the bins its walk reached.
+extern "C" int mcg_score_member_items(mcg_ctx *ctx, const int64_t *item_query,
+                                      const int32_t *item_bin, int64_t n_items,
+                                      const int64_t *members, const int64_t *seg_offsets,
+                                      int64_t nseg, int rule, double *weights) {
+    MCG_ENTER(ctx);
+    MCG_TRY(need_features(ctx));
+    if (n_items < 0 || nseg <= 0 || !seg_offsets || (rule != MCG_RULE_A && rule != MCG_RULE_B) ||
+        (n_items > 0 && (!item_query || !item_bin || !weights)))
+        return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    if (n_items == 0) return MCG_OK;
+    const int64_t nm = seg_offsets[nseg];
+    const int64_t limit = std::min(ctx->n_prof, ctx->n_cov);
+    if (seg_offsets[0] != 0) return mcg_fail(ctx, MCG_ERR_ARG, "seg_offsets[0] must be 0");
+    for (int64_t b = 0; b < nseg; ++b)
+        if (seg_offsets[b + 1] < seg_offsets[b])
+            return mcg_fail(ctx, MCG_ERR_ARG, "seg_offsets must not decrease");
+    MCG_TRY(check_ids(ctx, item_query, n_items, limit, "item_query"));
+    MCG_TRY(check_ids(ctx, members, nm, limit, "members"));
+    for (int64_t i = 0; i < n_items; ++i)
+        if (item_bin[i] < 0 || item_bin[i] >= nseg)
+            return mcg_fail(ctx, MCG_ERR_ARG, "item_bin[%lld] = %d outside 0..%lld", (long long)i,
+                            item_bin[i], (long long)nseg);
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(int64_t) * n_items));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(int64_t) * std::max<int64_t>(nm, 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[2], sizeof(int64_t) * (nseg + 1)));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[3], sizeof(int32_t) * n_items));
+    ctx->cand_valid = false;
+    ctx->redo_valid = false;
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[4], sizeof(double) * n_items));
+    MCG_TRY(h2d(ctx, ctx->scratch[0].p, item_query, sizeof(int64_t) * n_items));
+    MCG_TRY(h2d(ctx, ctx->scratch[1].p, members, sizeof(int64_t) * nm));
+    MCG_TRY(h2d(ctx, ctx->scratch[2].p, seg_offsets, sizeof(int64_t) * (nseg + 1)));
+    MCG_TRY(h2d(ctx, ctx->scratch[3].p, item_bin, sizeof(int32_t) * n_items));
+    {
+        TimerScope t(ctx, T_SCORE);
+        MCG_TRY(mcg_k_member_items(ctx, contig_side(ctx, nullptr, 0), ctx->scratch[0].as<int64_t>(),
+                                   ctx->scratch[3].as<int32_t>(), n_items,
+                                   ctx->scratch[1].as<int64_t>(), ctx->scratch[2].as<int64_t>(),
+                                   ctx->n_samples, rule, ctx->scratch[4].as<double>(),
+                                   ctx->status.as<int32_t>()));
+    }
+    MCG_TRY(d2h(ctx, weights, ctx->scratch[4].p, sizeof(double) * n_items));
+    return mcg_check_status(ctx);
+}
+
 extern "C" int mcg_path_lengths(mcg_ctx *ctx, const int64_t *indptr, const int32_t *indices,
                                 int64_t n_vertices, const int64_t *sources, int64_t n_sources,
                                 const int64_t *targets, int64_t n_targets, int32_t *out) {
@@ -1278,10 +1518,10 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
     MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples));
     MCG_TRY(set_centroids_locked(ctx, cen_prof, cen_cov, n_bins, n_samples));
     MCG_MARK("cov+centroids queued");
-    if (encoding == MCG_ENC_ASCII && offsets && offsets[n] >= (64 << 20) && !getenv("MCG_NO_WAVES")) {
-        // Large ASCII loads: every contig range is scanned, normalised and scored as soon as
-        // its packed words are complete in stream order, while the rest is still uploading;
-        // after the last copy only the last range is left to do.
+    if (offsets && offsets[n] >= (64 << 20) && !getenv("MCG_NO_WAVES")) {
+        // Large loads (ASCII or 2 bit): every contig range is scanned, normalised and scored as
+        // soon as its packed words are complete in stream order, while the rest is still
+        // uploading; after the last copy only the last range is left to do.
         MCG_TRY(cov_terms_locked(ctx));
         MCG_TRY(mcg_reserve(ctx, ctx->counts, sizeof(uint32_t) * MCG_NPROF * n));
         MCG_TRY(mcg_reserve(ctx, ctx->prof, sizeof(double) * MCG_NPROF * n));
@@ -1315,7 +1555,7 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
                     // the kernels the whole set would take in one call (two-kernel path from
                     // 2048 contigs), whatever the size of the range: the weights must not
                     // depend on where the upload happened to cut the waves
-                    ctx->force_split = n >= 2048;
+                    ctx->force_split = n >= 2048 || ctx->force_split_calls;
                     rc = mcg_k_pairs(ctx, a, centroid_side(ctx), ctx->n_samples, out,
                                      ctx->status.as<int32_t>());
                     ctx->force_split = false;
@@ -1399,6 +1639,39 @@ extern "C" int mcg_pack_2bit_host(const uint8_t *bases, const int64_t *offsets, 
     }
     if (n > 0 && offsets[n] > offsets[0] && !bases) return MCG_ERR_ARG;
     mcg_hostpack_range(bases, offsets, 0, n, first.data(), sizeof(int64_t), packed, level);
+    return MCG_OK;
+}
+
+// The same with `threads` host threads over contig ranges of equal bases (<= 0: all hardware
+// threads): what a FASTA reader calls once at parse time so that later uploads carry 2 bits per base.
+extern "C" int mcg_pack_2bit_host_mt(const uint8_t *bases, const int64_t *offsets, int64_t n,
+                                     uint8_t *packed, int threads) {
+    if (n < 0 || (n > 0 && (!offsets || !packed))) return MCG_ERR_ARG;
+    if (n == 0) return MCG_OK;
+    std::vector<int64_t> first(static_cast<size_t>(n) + 1, 0);
+    for (int64_t c = 0; c < n; ++c) {
+        const int64_t len = offsets[c + 1] - offsets[c];
+        if (len < 0) return MCG_ERR_ARG;
+        first[c + 1] = first[c] + 4 * ((len + 63) / 64);
+    }
+    if (offsets[n] > offsets[0] && !bases) return MCG_ERR_ARG;
+    if (threads <= 0) threads = static_cast<int>(std::thread::hardware_concurrency());
+    const int64_t total = offsets[n] - offsets[0];
+    if (threads > 1 && total < (8 << 20)) threads = 1;
+    std::vector<int64_t> cut(static_cast<size_t>(threads) + 1, n);
+    cut[0] = 0;
+    for (int t = 1; t < threads; ++t)
+        cut[t] = std::lower_bound(offsets, offsets + n + 1, offsets[0] + total / threads * t) - offsets;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t)
+        pool.emplace_back([&, t]() {
+            if (cut[t + 1] > cut[t])
+                mcg_hostpack_range(bases, offsets, cut[t], cut[t + 1], first.data(), sizeof(int64_t),
+                                   packed, -1);
+        });
+    if (cut[1] > cut[0])
+        mcg_hostpack_range(bases, offsets, cut[0], cut[1], first.data(), sizeof(int64_t), packed, -1);
+    for (std::thread &t : pool) t.join();
     return MCG_OK;
 }
 

@@ -115,6 +115,250 @@ int mcg_k_bfs(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices, i
     return MCG_OK;
 }
 
+// ---- the same walk over a RESIDENT graph, hits as flat lists ------------------------------------
+//
+// label_prop_utils.py:448-511 re-runs run_bfs_long for the few contigs around every accepted
+// contig.  With the CSR graph and the labels resident in the context (mcg_graph_load,
+// mcg_labels_load / mcg_labels_set) such a call moves only its start nodes and its hits, and a
+// stage with millions of start nodes needs no per-start output slots: every walk buffers its
+// hits, reserves a range of one flat list with a single atomicAdd when it ends, and copies
+// them there (same pop order).  The visited / depth table of a walk sits in SHARED memory
+// (128 slots per walk, slot-major so that the threads of a warp use different banks for the
+// same slot): bounded walks touch tens of vertices, and the table was what the first version
+// paid global-memory latency for.  A walk that does not fit (table 3/4 full, queue or hit
+// buffer full) is listed and repeated by the same code over a table in global memory.
+namespace {
+
+constexpr int kWalkThreads = 64;
+constexpr int kWalkSlots = 128;                 // shared table slots per walk
+constexpr int kWalkQueue = 384;                 // queue entries per walk
+constexpr int kWalkHits = 64;                   // buffered hits per walk
+constexpr int kWalkSlice = kWalkQueue + 2 * kWalkHits;   // int32 of global work space per walk
+
+struct WalkOut {
+    long long *total;        // [1] entries of the flat list reserved so far (may pass cap)
+    int *n_redo;             // [1]
+    int32_t *redo;           // walks that did not fit (index into starts)
+    long long *start;        // [n_starts] first entry of the walk's hits
+    int32_t *count;          // [n_starts] hits of the walk; -2 while it waits in `redo`
+    int32_t *hits;           // [cap][3] (labelled node, bin, depth)
+    long long cap;
+};
+
+struct SharedTable {
+    int2 *base;              // this thread's column: slot s at base[s * kWalkThreads]
+    int used;
+    __device__ __forceinline__ int capacity() const { return kWalkSlots; }
+    __device__ __forceinline__ int limit() const { return kWalkSlots * 3 / 4; }
+    __device__ __forceinline__ int2 &at(int pos) { return base[pos * kWalkThreads]; }
+};
+
+struct GlobalTable {
+    int2 *base;
+    int cap;                 // power of two
+    int used;
+    __device__ __forceinline__ int capacity() const { return cap; }
+    __device__ __forceinline__ int limit() const { return cap / 4 * 3; }
+    __device__ __forceinline__ int2 &at(int pos) { return base[pos]; }
+};
+
+// slot of `vertex` (x = vertex + 1, y = depth << 1 | visited), inserted if absent; -1 = full
+template <class Table> __device__ __forceinline__ int table_slot(Table &tb, int vertex) {
+    const int mask = tb.capacity() - 1;
+    int pos = static_cast<int>(((static_cast<uint32_t>(vertex) * 2654435761u) >> 7) & mask);
+    for (int probes = 0; probes <= mask; ++probes) {
+        const int key = tb.at(pos).x;
+        if (key == vertex + 1) return pos;
+        if (key == 0) {
+            if (tb.used >= tb.limit()) return -1;
+            tb.at(pos) = make_int2(vertex + 1, 0);
+            ++tb.used;
+            return pos;
+        }
+        pos = (pos + 1) & mask;
+    }
+    return -1;
+}
+
+// One bounded walk (label_prop_utils.py:37-53, 92-100).  Hits go to tmp as (node, depth) pairs.
+// Returns the number of hits, or -1 when a table / queue / hit buffer was too small.
+template <class Table>
+__device__ int walk_one(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                        const int32_t *__restrict__ labels, int start, int depth_limit,
+                        int32_t *queue, int queue_cap, int32_t *tmp, int tmp_cap, Table &tb) {
+    int head = 0, tail = 0, n_visited = 0, hits = 0;
+    queue[tail++] = start;
+    if (table_slot(tb, start) < 0) return -1;
+    while (head < tail) {
+        const int v = queue[head++];
+        const int sv = table_slot(tb, v);
+        if (sv < 0) return -1;
+        int val = tb.at(sv).y;
+        if (!(val & 1)) { val |= 1; tb.at(sv).y = val; ++n_visited; }
+        const int dv = val >> 1;
+        if (labels[v] >= 0 && n_visited > 1) {
+            if (hits >= tmp_cap) return -1;
+            tmp[2 * hits] = v;
+            tmp[2 * hits + 1] = dv;
+            ++hits;
+            continue;
+        }
+        for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) {
+            const int nb = indices[e];
+            const int sn = table_slot(tb, nb);
+            if (sn < 0) return -1;
+            if (tb.at(sn).y & 1) continue;                 // already visited
+            tb.at(sn).y = (dv + 1) << 1;                   // depth overwrite, visited = 0
+            if (dv + 1 > depth_limit) continue;
+            if (tail >= queue_cap) return -1;
+            queue[tail++] = nb;
+        }
+    }
+    return hits;
+}
+
+__device__ __forceinline__ void walk_emit(const WalkOut &out, long long i, int hits,
+                                          const int32_t *tmp, const int32_t *__restrict__ labels) {
+    const long long base = hits ? atomicAdd(reinterpret_cast<unsigned long long *>(out.total),
+                                            static_cast<unsigned long long>(hits)) : 0;
+    out.start[i] = base;
+    out.count[i] = hits;
+    if (base + hits > out.cap) return;   // the caller sees total > cap and comes back
+    for (int h = 0; h < hits; ++h) {
+        int32_t *o = out.hits + 3 * (base + h);
+        o[0] = tmp[2 * h];
+        o[1] = labels[tmp[2 * h]];
+        o[2] = tmp[2 * h + 1];
+    }
+}
+
+__global__ void __launch_bounds__(kWalkThreads)
+walk_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+            const int32_t *__restrict__ labels, const int64_t *__restrict__ starts,
+            long long first, long long n_starts, int depth_limit, int32_t *__restrict__ work,
+            WalkOut out) {
+    extern __shared__ int2 walk_tab[];
+    const int t = threadIdx.x;
+    for (int s = 0; s < kWalkSlots; ++s) walk_tab[s * kWalkThreads + t].x = 0;
+    const long long local = blockIdx.x * static_cast<long long>(kWalkThreads) + t;
+    const long long i = first + local;
+    if (i >= n_starts) return;
+    int32_t *queue = work + local * kWalkSlice;
+    int32_t *tmp = queue + kWalkQueue;
+    SharedTable tb = {walk_tab + t, 0};
+    const int hits = walk_one(indptr, indices, labels, static_cast<int>(starts[i]), depth_limit,
+                              queue, kWalkQueue, tmp, kWalkHits, tb);
+    if (hits < 0) {
+        out.count[i] = -2;
+        out.redo[atomicAdd(out.n_redo, 1)] = static_cast<int32_t>(i);
+        return;
+    }
+    walk_emit(out, i, hits, tmp, labels);
+}
+
+// The listed walks again, table / queue / hit buffer in a slice of global memory (stride a power
+// of two >= 1024 int32): [queue stride/2][hits 2 x stride/16][table 2 x stride/8 slots].
+__global__ void __launch_bounds__(64)
+walk_redo_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                 const int32_t *__restrict__ labels, const int64_t *__restrict__ starts,
+                 int n_redo, int depth_limit, int32_t *__restrict__ work, long long stride,
+                 WalkOut out, int *__restrict__ n_failed) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_redo) return;
+    const long long i = out.redo[j];
+    if (out.count[i] != -2) return;      // done by an earlier pass
+    const int q = static_cast<int>(stride / 2), h = static_cast<int>(stride / 16),
+              c = static_cast<int>(stride / 8);
+    int32_t *queue = work + j * stride;
+    int32_t *tmp = queue + q;
+    GlobalTable tb = {reinterpret_cast<int2 *>(tmp + 2 * h), c, 0};
+    for (int s = 0; s < c; ++s) tb.base[s].x = 0;
+    const int hits = walk_one(indptr, indices, labels, static_cast<int>(starts[i]), depth_limit,
+                              queue, q, tmp, h, tb);
+    if (hits < 0) { atomicAdd(n_failed, 1); return; }
+    walk_emit(out, i, hits, tmp, labels);
+}
+
+__global__ void labels_set_kernel(int32_t *__restrict__ labels, const int64_t *__restrict__ ids,
+                                  const int32_t *__restrict__ bins, long long n) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i < n) labels[ids[i]] = bins[i];
+}
+
+}  // namespace
+
+int mcg_k_labels_set(mcg_ctx *ctx, int32_t *d_labels, const int64_t *d_ids, const int32_t *d_bins,
+                     int64_t n) {
+    if (n == 0) return MCG_OK;
+    labels_set_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
+        d_labels, d_ids, d_bins, n);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int64_t mcg_walk_chunk(void) { return 131072; }
+size_t mcg_walk_work_bytes(int64_t n_starts) {
+    const int64_t chunk = n_starts < mcg_walk_chunk() ? n_starts : mcg_walk_chunk();
+    const int64_t padded = (chunk + kWalkThreads - 1) / kWalkThreads * kWalkThreads;
+    return sizeof(int32_t) * static_cast<size_t>(padded) * kWalkSlice;
+}
+
+// block: [total i64][n_redo i32][n_failed i32][start i64 x n][count i32 x n (padded to 8 bytes)]
+//        [redo i32 x n (padded)][hits i32 x 3 cap]
+int mcg_k_walks(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
+                const int32_t *d_labels, const int64_t *d_starts, int64_t n_starts,
+                int depth_limit, int32_t *d_work, char *d_block, int64_t cap) {
+    static bool attr[64] = {};
+    const size_t smem = sizeof(int2) * kWalkSlots * kWalkThreads;
+    if (!(ctx->device < 64 && attr[ctx->device])) {
+        MCG_CUDA(ctx, cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+        if (ctx->device < 64) attr[ctx->device] = true;
+    }
+    const int64_t n8 = (n_starts + 1) / 2 * 2;
+    WalkOut out;
+    out.total = reinterpret_cast<long long *>(d_block);
+    out.n_redo = reinterpret_cast<int *>(d_block + 8);
+    out.start = reinterpret_cast<long long *>(d_block + 16);
+    out.count = reinterpret_cast<int32_t *>(out.start + n_starts);
+    out.redo = out.count + n8;
+    out.hits = out.redo + n8;
+    out.cap = cap;
+    MCG_CUDA(ctx, cudaMemsetAsync(d_block, 0, 16, ctx->stream));
+    const int64_t chunk = mcg_walk_chunk();
+    for (int64_t first = 0; first < n_starts; first += chunk) {
+        const int64_t m = n_starts - first < chunk ? n_starts - first : chunk;
+        walk_kernel<<<static_cast<unsigned>((m + kWalkThreads - 1) / kWalkThreads), kWalkThreads,
+                      smem, ctx->stream>>>(d_indptr, d_indices, d_labels, d_starts, first,
+                                           n_starts, depth_limit, d_work, out);
+        MCG_KERNEL_CHECK(ctx);
+    }
+    return MCG_OK;
+}
+
+// The walks walk_kernel listed, with `stride` int32 of global work space each (n_redo known to
+// the host).  *d_block + 12 counts the walks that still did not fit.
+int mcg_k_walks_redo(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
+                     const int32_t *d_labels, const int64_t *d_starts, int64_t n_starts,
+                     int n_redo, int depth_limit, int32_t *d_work, int64_t stride, char *d_block,
+                     int64_t cap) {
+    const int64_t n8 = (n_starts + 1) / 2 * 2;
+    WalkOut out;
+    out.total = reinterpret_cast<long long *>(d_block);
+    out.n_redo = reinterpret_cast<int *>(d_block + 8);
+    out.start = reinterpret_cast<long long *>(d_block + 16);
+    out.count = reinterpret_cast<int32_t *>(out.start + n_starts);
+    out.redo = out.count + n8;
+    out.hits = out.redo + n8;
+    out.cap = cap;
+    MCG_CUDA(ctx, cudaMemsetAsync(d_block + 12, 0, 4, ctx->stream));
+    walk_redo_kernel<<<static_cast<unsigned>((n_redo + 63) / 64), 64, 0, ctx->stream>>>(
+        d_indptr, d_indices, d_labels, d_starts, n_redo, depth_limit, d_work, stride, out,
+        reinterpret_cast<int *>(d_block + 12));
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
 // ---- shortest-path lengths for the graph gate of match_contigs ----------------------------------
 //
 //   reference: matching_utils.py:191-197 and :285-292 call, for a matched contig v and every

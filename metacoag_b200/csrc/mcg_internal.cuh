@@ -80,11 +80,20 @@ struct mcg_ctx {
     DevBuf cen_norm;           // f64 [B]
     DevBuf cen_cov, cen_logc, cen_lgam;   // f64 [B,S]
 
+    // ---- assembly graph + labels, resident for a label-propagation stage ------------
+    int64_t g_vertices = 0, g_edges = 0;
+    DevBuf g_indptr, g_indices;   // int64 [V + 1], int32 [E]
+    DevBuf g_labels;              // int32 [V] bin of the contig or -1
+    DevBuf g_work, g_block, g_starts, g_patch;   // walk scratch (grow-only)
+    void *g_pinned = nullptr;     // pinned mirror of the head of g_block
+    size_t g_pinned_cap = 0;
+
     // ---- results / scratch ---------------------------------------------------------
     DevBuf argmin, wmin;       // int32 [n], f64 [n]
     DevBuf status;             // int32 [4] device-side flags (0: domain error)
     DevBuf scratch[6];
     bool force_split = false;  // rule C always on the two-kernel path (waves: results must not depend on batch size)
+    bool force_split_calls = false;   // the same across calls: set by the device pool around a sharded call
     bool cand_valid = false;   // scratch[3] starts with the candidate count of the last pruned rule-C chunk
     long long cand_cap = 0, cand_pairs = 0;
     bool redo_valid = false;   // scratch[4] starts with the redo count of the last guarded rule-C call
@@ -186,6 +195,10 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
 int mcg_k_aggregate_members(mcg_ctx *ctx, const double *d_lp, int64_t nq, int64_t nm,
                             const int64_t *d_seg_offsets, int64_t nseg, int rule,
                             double *d_weights);
+int mcg_k_member_items(mcg_ctx *ctx, const ScoreSide &table, const int64_t *d_item_query,
+                       const int32_t *d_item_bin, int64_t n_items, const int64_t *d_members,
+                       const int64_t *d_seg_offsets, int n_samples, int rule, double *d_weights,
+                       int32_t *d_status);
 int mcg_k_segment_mean(mcg_ctx *ctx, const double *d_rows, int width, const int64_t *d_members,
                        const int64_t *d_seg_offsets, int64_t nseg, double *d_out);
 int mcg_k_normpdf(mcg_ctx *ctx, const double *d_x, double mean, double sd, double *d_out,
@@ -204,6 +217,17 @@ int mcg_k_bfs(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices, i
               const int32_t *d_labels, const int64_t *d_starts, int64_t n_starts, int depth_limit,
               int max_hits, int32_t *d_hit_node, int32_t *d_hit_bin, int32_t *d_hit_depth,
               int32_t *d_n_hits, int32_t *d_work, int64_t work_stride);
+int mcg_k_labels_set(mcg_ctx *ctx, int32_t *d_labels, const int64_t *d_ids, const int32_t *d_bins,
+                     int64_t n);
+int64_t mcg_walk_chunk(void);
+size_t mcg_walk_work_bytes(int64_t n_starts);
+int mcg_k_walks(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
+                const int32_t *d_labels, const int64_t *d_starts, int64_t n_starts,
+                int depth_limit, int32_t *d_work, char *d_block, int64_t cap);
+int mcg_k_walks_redo(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
+                     const int32_t *d_labels, const int64_t *d_starts, int64_t n_starts,
+                     int n_redo, int depth_limit, int32_t *d_work, int64_t stride, char *d_block,
+                     int64_t cap);
 int mcg_k_components(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices,
                      int64_t n, int32_t *d_work, int *d_flag, int32_t *d_labels);
 int mcg_path_words(int64_t ns);   // mask words per vertex; work space = (4 W + 3) n int32

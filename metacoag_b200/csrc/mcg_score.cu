@@ -726,9 +726,13 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
                     pv = LOGSUM ? exp_core(pmin, ET) : pmin;
                     if (pc != pc) domain_error = true;
                     valid = __dmul_rn(pc, pv) > 0.0;
-                    if (valid) {   // -(log(pc, 10) + log(pv, 10))
+                    if (valid) {
+                        // -(math.log(pc, 10) + math.log(pv, 10)): CPython's two-argument log is
+                        // log(x) / log(10) per term, so two divisions, then the sum (rules A / B
+                        // feed hard comparisons: <= w_intra, > w_inter, first-minimum argmin)
                         const double log_pv = LOGSUM ? pmin : log_core(pv, LT);
-                        lp = -(log_core(pc, LT) + log_pv) * c_math.inv_ln10;
+                        lp = -(__ddiv_rn(log_core(pc, LT), c_gauss.ln10) +
+                               __ddiv_rn(log_pv, c_gauss.ln10));
                     }
                 }
                 const long long o = ar * B.n + bc;
@@ -1557,6 +1561,97 @@ __global__ void aggregate_members_kernel(const double *__restrict__ lp, long lon
     weights[i] = w;
 }
 
+// Rules A / B for LISTED (query, bin) items.  label_prop_utils.py:54-86 scores a candidate only
+// against the bins its walk reached (a handful of the B bins), so at scale the dense
+// [queries, bins] form above does hundreds of times the work the reference does.  One warp per
+// item walks the bin's members in order: squared distance in the reference's difference form
+// (matching_utils.py:28-29; lanes over the 136 slots), prob_comp, the Poisson terms with one
+// sample per lane and the running sums / products taken in sample order through shuffles
+// (sums of floored exponents for S <= 30, in-order products beyond, exactly like pair_kernel),
+// the reference's -(log(pc)/log 10 + log(pv)/log 10), and the member sum with MAX + finite = MAX,
+// MAX + MAX = inf.
+__global__ void __launch_bounds__(256)
+member_items_kernel(ScoreSide T, const int64_t *__restrict__ item_query,
+                    const int32_t *__restrict__ item_bin, long long n_items,
+                    const int64_t *__restrict__ members, const int64_t *__restrict__ seg_offsets,
+                    int S, int rule, double *__restrict__ weights, int32_t *__restrict__ status) {
+    __shared__ double ET[16];
+    __shared__ double LT[128];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 16) ET[tid] = g_exp_table[tid];
+    if (tid < 128) LT[tid] = g_log_table[tid];
+    __syncthreads();
+    const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    const bool logsum = S <= 30;
+    for (long long it = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (tid >> 5);
+         it < n_items; it += n_warps) {
+        const long long q = item_query[it];
+        const int b = item_bin[it];
+        const long long lo = seg_offsets[b], hi = seg_offsets[b + 1];
+        const double *u = T.prof + q * MCG_NPROF;
+        double ur[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) ur[i] = (lane + 32 * i < MCG_NPROF) ? u[lane + 32 * i] : 0.0;
+        double sum = 0.0;
+        long long n_valid = 0;
+        bool domain = false;
+        for (long long j = lo; j < hi; ++j) {
+            const long long m = members[j];
+            const double *v = T.prof + m * MCG_NPROF;
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const double d = ur[i] - ((lane + 32 * i < MCG_NPROF) ? v[lane + 32 * i] : 0.0);
+                acc = fma(d, d, acc);
+            }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, w);
+            const double pc = comp_prob_fast(acc, ET);
+            if (pc != pc) domain = true;
+            // cov1 = the query, cov2 = the member (label_prop_utils.py:66-68)
+            double p1 = logsum ? 0.0 : 1.0, p2 = p1;
+            for (int s0 = 0; s0 < S; s0 += 32) {
+                const int s = s0 + lane;
+                double t1 = 0.0, t2 = 0.0;
+                if (s < S) {
+                    const double ac = T.cov[q * S + s], al = T.logc[q * S + s], ag = T.lgam[q * S + s];
+                    const double bc = T.cov[m * S + s], bl = T.logc[m * S + s], bg = T.lgam[m * S + s];
+                    t1 = poisson_exponent(ac, ag, bc, bl);
+                    t2 = poisson_exponent(bc, bg, ac, al);
+                    if (!logsum) { t1 = exp_core(t1, ET); t2 = exp_core(t2, ET); }
+                }
+                const int sc = S - s0 < 32 ? S - s0 : 32;
+                for (int k = 0; k < sc; ++k) {
+                    const double a1 = __shfl_sync(0xffffffffu, t1, k);
+                    const double a2 = __shfl_sync(0xffffffffu, t2, k);
+                    if (logsum) { p1 = __dadd_rn(p1, a1); p2 = __dadd_rn(p2, a2); }
+                    else { p1 = __dmul_rn(p1, a1); p2 = __dmul_rn(p2, a2); }
+                }
+            }
+            const double pmin = p1 < p2 ? p1 : p2;
+            const double pv = logsum ? exp_core(pmin, ET) : pmin;
+            double lp = MCG_MAX_WEIGHT;
+            if (__dmul_rn(pc, pv) > 0.0) {
+                const double log_pv = logsum ? pmin : log_core(pv, LT);
+                lp = -(__ddiv_rn(log_core(pc, LT), c_gauss.ln10) + __ddiv_rn(log_pv, c_gauss.ln10));
+                ++n_valid;
+            }
+            sum = __dadd_rn(sum, lp);
+        }
+        if (lane == 0) {
+            double w;
+            if (rule == MCG_RULE_A)
+                w = (sum != INFINITY && hi > lo) ? __ddiv_rn(sum, static_cast<double>(hi - lo))
+                                                 : MCG_MAX_WEIGHT;
+            else
+                w = (sum != INFINITY && n_valid != 0) ? __ddiv_rn(sum, static_cast<double>(n_valid))
+                                                      : MCG_MAX_WEIGHT;
+            weights[it] = w;
+            if (domain) atomicOr(status, 1);
+        }
+    }
+}
+
 // feature_utils.py:232-233 np.mean(rows, axis=0): rows added in member order, one division.
 __global__ void segment_mean_kernel(const double *__restrict__ rows, int width,
                                     const int64_t *__restrict__ members,
@@ -1970,7 +2065,8 @@ int mcg_k_pairs(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, int n_samp
     // big rule-C batches: distance GEMM + probability kernel (argmin/wmin are needed to
     // carry the running minimum when the bins do not fit one shared-memory group)
     // (S > 30: only without the weight matrix -- deferred pairs have no exact weight there)
-    if (rule_c && (a.n >= 2048 || ctx->force_split) && out.argmin && out.wmin &&
+    if (rule_c && (a.n >= 2048 || ctx->force_split || ctx->force_split_calls) && out.argmin &&
+        out.wmin &&
         (logsum || (!out.weights && split_fits(n_samples))))
         return split_rule_c(ctx, a, b, n_samples, out, d_status);
     if (out.dist) {
@@ -1997,6 +2093,21 @@ int mcg_k_aggregate_members(mcg_ctx *ctx, const double *d_lp, int64_t nq, int64_
     if (nq * nseg == 0) return MCG_OK;
     aggregate_members_kernel<<<blocks_for(nq * nseg, 128), 128, 0, ctx->stream>>>(
         d_lp, nq, nm, d_seg_offsets, nseg, rule, d_weights);
+    MCG_KERNEL_CHECK(ctx);
+    return MCG_OK;
+}
+
+int mcg_k_member_items(mcg_ctx *ctx, const ScoreSide &table, const int64_t *d_item_query,
+                       const int32_t *d_item_bin, int64_t n_items, const int64_t *d_members,
+                       const int64_t *d_seg_offsets, int n_samples, int rule, double *d_weights,
+                       int32_t *d_status) {
+    MCG_TRY(ensure_gauss(ctx));
+    if (n_items == 0) return MCG_OK;
+    long long blocks = (n_items + 7) / 8;
+    if (blocks > 16LL * ctx->sm_count) blocks = 16LL * ctx->sm_count;
+    member_items_kernel<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(
+        table, d_item_query, d_item_bin, n_items, d_members, d_seg_offsets, n_samples, rule,
+        d_weights, d_status);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
 }

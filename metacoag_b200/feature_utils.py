@@ -60,11 +60,15 @@ class ContigBlob:
     ``sequences`` list (``len``, indexing, slicing and iteration give ``str``): what
     get_cov_len / get_cov_len_megahit return here.  get_tetramer_profiles hands ``blob`` and
     ``offsets`` to the C ABI as they are instead of joining 10^5..10^6 Python strings
-    (SURVEY.md 8f item 1)."""
+    (SURVEY.md 8f item 1).  The ASCII bytes stay: the writer of the per-bin FASTA files
+    (metacoag:1236-1251) needs them."""
 
-    def __init__(self, blob, offsets):
+    def __init__(self, blob, offsets, packed=None):
         self.blob = blob
         self.offsets = np.asarray(offsets, dtype=np.int64)
+        # the same contigs in the library's 2-bit layout, packed once at parse time: every later
+        # upload (get_tetramer_profiles) carries a quarter of the bytes
+        self.packed = packed
 
     def __len__(self):
         return self.offsets.shape[0] - 1
@@ -141,16 +145,26 @@ def get_tetramer_profiles(output_path, sequences, contigs_file, contig_lengths, 
     if os.path.isfile(cache):
         with open(cache, "rb") as handle:
             normalized = pickle.load(handle)
+        dense = None
     else:
         blob, offsets = _ascii_blob(sequences)
+        packed = getattr(sequences, "packed", None)
+        if packed is not None and blob is not sequences.blob:
+            packed = None          # the blob was rebuilt (strip): the parse-time packing is stale
         if len(sequences):
-            _, freqs = _backend.backend().tetramer_scan(blob, offsets)
+            _, freqs = _backend.backend().tetramer_scan(blob, offsets, packed=packed)
         else:
             freqs = np.zeros((0, _lib.NPROF))
-        normalized = {i: freqs[i] for i in range(freqs.shape[0])}
+        normalized = {i: row for i, row in enumerate(freqs)}
         with open(cache, "wb") as handle:
             pickle.dump(normalized, handle, protocol=pickle.HIGHEST_PROTOCOL)
-    return {i: normalized[i] for i in range(len(normalized)) if contig_lengths[i] >= min_length}
+        dense = freqs
+    # the reference's dict of the long contigs; it remembers the dense table it is a view of,
+    # so that staging it for the scorers is not a Python loop over contigs (_backend.stage)
+    table = _backend.ProfileTable((i, normalized[i]) for i in range(len(normalized))
+                                  if contig_lengths[i] >= min_length)
+    table.dense = dense
+    return table
 
 
 def _fasta_records(path):
@@ -176,8 +190,12 @@ def _read_contigs(contigs_file):
     """(names, sequences) of a FASTA file through the library's host reader: the sequences
     come back as a ContigBlob (pinned when a CUDA device is there, so that the upload needs
     no staging copy)."""
-    names, blob, offsets = _lib.read_fasta(contigs_file, pinned=_lib.device_count() > 0)
-    return names, ContigBlob(blob, offsets)
+    on_device = _lib.device_count() > 0
+    names, blob, offsets = _lib.read_fasta(contigs_file, pinned=on_device)
+    packed = None
+    if on_device and blob.shape[0]:
+        packed = _lib.pack_2bit_host(blob, offsets, threads=0, pinned=True)
+    return names, ContigBlob(blob, offsets, packed)
 
 
 def _read_abundance(abundance_file, contig_num_of, contig_lengths, min_length, coverages):
@@ -208,6 +226,7 @@ def get_cov_len(contigs_file, contig_names_rev, min_length, abundance_file):
     """``(sequences, coverages, contig_lengths, n_samples)`` (:122-165).  ``coverages`` is a
     ``defaultdict(lambda: [0])`` and ``contig_lengths`` a ``defaultdict(int)`` like the
     reference's; an unknown contig name raises KeyError."""
+    _backend.reset()      # a pipeline run starts here: nothing staged by an earlier run survives
     coverages = defaultdict(lambda: [0])
     contig_lengths = defaultdict(int)
     names, sequences = _read_contigs(contigs_file)
@@ -221,6 +240,7 @@ def get_cov_len(contigs_file, contig_names_rev, min_length, abundance_file):
 def get_cov_len_megahit(contigs_file, contig_names_rev, graph_to_contig_map_rev, min_length,
                         abundance_file):
     """MEGAHIT flavour: FASTA names map to graph names first (:168-214)."""
+    _backend.reset()
     coverages, contig_lengths = {}, {}
     names, sequences = _read_contigs(contigs_file)
     for name, length in zip(names, np.diff(sequences.offsets).tolist()):

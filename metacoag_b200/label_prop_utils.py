@@ -37,46 +37,63 @@ _vertex_count = _backend.vertex_count
 class _SeedScores:
     """Rule-B score of (node, bin): mean -log10 score against the first
     ``smg_bin_counts[bin]`` members of the bin (:54-86).  Those members never change during a
-    stage, so the score is computed once per node, for all bins in one launch."""
+    stage, so a score is computed once; like the reference, only the bins a node's walk
+    reached are scored (one launch per batch of new (node, bin) items)."""
 
     def __init__(self, bins, smg_bin_counts, profiles, coverages):
         self.order = list(bins)
         self.col = {b: i for i, b in enumerate(self.order)}
         self.members, self.seg = _backend.csr_bins(bins, self.order, smg_bin_counts)
         self.profiles, self.coverages = profiles, coverages
-        self.rows = {}
+        self.cache = {}
 
-    def ensure(self, nodes):
-        todo = [n for n in dict.fromkeys(int(x) for x in nodes) if n not in self.rows]
+    def ensure(self, items):
+        todo = [it for it in dict.fromkeys(items) if it not in self.cache]
         if todo:
-            w = _backend.backend().score_members(self.profiles, self.coverages,
-                                                 np.asarray(todo, dtype=np.int64), self.members,
-                                                 self.seg, RULE_B)
-            for i, n in enumerate(todo):
-                self.rows[n] = w[i]
+            query = np.fromiter((it[0] for it in todo), dtype=np.int64, count=len(todo))
+            col = np.fromiter((self.col[it[1]] for it in todo), dtype=np.int32, count=len(todo))
+            w = _backend.backend().score_member_items(self.profiles, self.coverages, query, col,
+                                                      self.members, self.seg, RULE_B)
+            self.cache.update(zip(todo, w.tolist()))
 
     def get(self, node, bin_):
-        return float(self.rows[node][self.col[bin_]])
+        return self.cache[(node, bin_)]
 
 
-def _bfs_hits(nodes, threshold, bin_of_contig, assembly_graph, n_vertices):
-    """For every start node the (labelled node, bin, depth) triples of run_bfs_long, in the
-    reference's pop order."""
-    indptr, indices = _graphs.get(assembly_graph, n_vertices)
-    labels = np.full(n_vertices, -1, dtype=np.int32)
-    for contig, b in bin_of_contig.items():
-        labels[contig] = b
-    starts = np.asarray(list(nodes), dtype=np.int64)
-    node, bin_, depth, n_hits = _backend.backend().bfs_candidates(indptr, indices, labels, starts,
-                                                                  threshold)
-    return [[(int(node[i, h]), int(bin_[i, h]), int(depth[i, h])) for h in range(int(n_hits[i]))]
-            for i in range(starts.shape[0])]
+class _Frontier:
+    """The assembly graph and the labels of one propagation stage, resident in the back end:
+    the CSR graph goes up once per graph, the labels once per stage, and every acceptance
+    patches ONE label (:270-271, :472-473) instead of rebuilding and re-sending both."""
+
+    def __init__(self, assembly_graph, n_vertices, bin_of_contig):
+        self.indptr, self.indices = _graphs.get(assembly_graph, n_vertices)
+        labels = np.full(n_vertices, -1, dtype=np.int32)
+        if len(bin_of_contig):
+            ids = np.fromiter(bin_of_contig.keys(), dtype=np.int64, count=len(bin_of_contig))
+            labels[ids] = np.fromiter(bin_of_contig.values(), dtype=np.int32,
+                                      count=len(bin_of_contig))
+        self.labels = labels
+        self.backend = _backend.backend()
+        self.backend.frontier(self.indptr, self.indices, _graphs.version, labels)
+
+    def patch(self, contig, bin_):
+        self.labels[contig] = bin_
+        self.backend.frontier_patch([contig], [bin_])
+
+    def walks(self, nodes, threshold):
+        """Per start node the (labelled node, bin, depth) triples of run_bfs_long, pop order."""
+        starts = np.asarray(list(nodes), dtype=np.int64)
+        if starts.shape[0] == 0:
+            return []
+        first, count, hits = self.backend.frontier_walks(starts, threshold)
+        rows = hits.tolist()
+        return [rows[a:a + c] for a, c in zip(first.tolist(), count.tolist())]
 
 
-def _local_candidates(nodes, threshold, bin_of_contig, scores, assembly_graph, n_vertices):
+def _local_candidates(nodes, threshold, frontier, scores):
     """(node, labelled, bin, depth, score) rows of ``nodes``, hits in pop order."""
-    hits = _bfs_hits(nodes, threshold, bin_of_contig, assembly_graph, n_vertices)
-    scores.ensure(n for n, h in zip(nodes, hits) if h)
+    hits = frontier.walks(nodes, threshold)
+    scores.ensure((n, b) for n, node_hits in zip(nodes, hits) for _, b, _ in node_hits)
     rows = []
     for n, node_hits in zip(nodes, hits):
         for labelled, b, d in node_hits:
@@ -93,29 +110,28 @@ def _distributed_world():
     return parallel.world()
 
 
-def _candidates(nodes, threshold, bin_of_contig, scores, assembly_graph, n_vertices):
+def _candidates(nodes, threshold, frontier, scores):
     """``[set of (node, labelled, bin, depth, score)]`` per node, the sets built by inserting
-    the hits in pop order like the reference does (:88-90).  With several ranks
+    the hits in pop order like the reference does (:88-90).  A single process spreads the start
+    nodes over its GPUs inside the library (mcg_pool_bfs).  With several PROCESSES
     (torch.distributed initialised) large batches are sharded: every rank walks and scores a
     slice of the nodes and the rows are all-gathered (metacoag_b200/parallel.py)."""
-    nodes = list(nodes)
+    nodes = [int(n) for n in nodes]
+    if not nodes:
+        return []
+    rows = None
     if _distributed_world() > 1:
         from . import parallel
         if len(nodes) >= parallel.MIN_SHARDED_NODES:
             lo, hi = parallel.shard_slice(len(nodes))
-            mine = _local_candidates(nodes[lo:hi], threshold, bin_of_contig, scores,
-                                     assembly_graph, n_vertices)
+            mine = _local_candidates(nodes[lo:hi], threshold, frontier, scores)
             ints = np.array([r[:4] for r in mine], dtype=np.int64).reshape(-1, 4)
             floats = np.array([[r[4]] for r in mine], dtype=np.float64).reshape(-1, 1)
             ints, floats = parallel.all_gather_rows(ints, floats)
             rows = [(int(a), int(b), int(c), int(d), float(f[0])) for (a, b, c, d), f
                     in zip(ints.tolist(), floats.tolist())]
-        else:
-            rows = _local_candidates(nodes, threshold, bin_of_contig, scores, assembly_graph,
-                                     n_vertices)
-    else:
-        rows = _local_candidates(nodes, threshold, bin_of_contig, scores, assembly_graph,
-                                 n_vertices)
+    if rows is None:
+        rows = _local_candidates(nodes, threshold, frontier, scores)
     by_node = {}
     for row in rows:
         by_node.setdefault(row[0], set()).add(row)
@@ -129,14 +145,15 @@ def run_bfs_long(node, threhold, binned_contigs, bin_of_contig, bins, smg_bin_co
     n_vertices = _vertex_count(assembly_graph, bin_of_contig, normalized_tetramer_profiles,
                                {node: 0})
     scores = _SeedScores(bins, smg_bin_counts, normalized_tetramer_profiles, coverages)
-    return _candidates([node], threhold, bin_of_contig, scores, assembly_graph, n_vertices)[0]
+    frontier = _Frontier(assembly_graph, n_vertices, bin_of_contig)
+    return _candidates([node], threhold, frontier, scores)[0]
 
 
 def run_bfs_short(node, threhold, binned_contigs, bin_of_contig, assembly_graph, coverages):
     """Never called by the pipeline; kept for the interface.
     Same traversal, score = Euclidean distance of the coverage vectors (:103-141)."""
     n_vertices = _vertex_count(assembly_graph, bin_of_contig, {node: 0})
-    hits = _bfs_hits([node], threhold, bin_of_contig, assembly_graph, n_vertices)[0]
+    hits = _Frontier(assembly_graph, n_vertices, bin_of_contig).walks([node], threhold)[0]
     found = set()
     for labelled, b, d in hits:
         dist = float(_backend.backend().tetramer_distance(
@@ -183,9 +200,12 @@ def _propagate(bin_of_contig, bins, contig_markers, bin_markers, binned_contigs_
         contigs_to_bin.update(_closest_long(assembly_graph, contig, bin_of_contig, contig_lengths,
                                             min_length))
 
+    if not contigs_to_bin:     # nothing to propagate to (label_prop as shipped)
+        return bins, bin_of_contig, bin_markers, binned_contigs_with_markers
+    frontier = _Frontier(assembly_graph, n_vertices, bin_of_contig)
+
     heap = []
-    for found in _candidates(contigs_to_bin, depth, bin_of_contig, scores, assembly_graph,
-                             n_vertices):
+    for found in _candidates(contigs_to_bin, depth, frontier, scores):
         for data in list(found):
             heapq.heappush(heap, DataWrap(data))
 
@@ -208,6 +228,7 @@ def _propagate(bin_of_contig, bins, contig_markers, bin_markers, binned_contigs_
 
         bins[bin_].append(to_bin)
         bin_of_contig[to_bin] = bin_
+        frontier.patch(to_bin, bin_)
         if has_mg:
             binned_contigs_with_markers.append(to_bin)
             bin_markers[bin_] = list(set(bin_markers[bin_] + contig_markers[to_bin]))
@@ -215,10 +236,11 @@ def _propagate(bin_of_contig, bins, contig_markers, bin_markers, binned_contigs_
         # the contigs around the new member get fresh candidates
         around = set(_closest_long(assembly_graph, to_bin, bin_of_contig, contig_lengths,
                                    min_length))
+        # (filter + heapify also when `around` is empty: heapify re-arranges entries with equal
+        # keys, and the pop order of ties is the reference's only with the same call sequence)
         heap = [x for x in heap if x.data[0] not in around]
         heapq.heapify(heap)
-        for found in _candidates(around, depth, bin_of_contig, scores, assembly_graph,
-                                 n_vertices):
+        for found in _candidates(around, depth, frontier, scores):
             for data in list(found):
                 heapq.heappush(heap, DataWrap(data))
 
@@ -249,20 +271,28 @@ def label_prop(bin_of_contig, bins, contig_markers, bin_markers, binned_contigs_
 class _CentroidCache:
     """assign_long is called once per contig, from several threads (metacoag:959-999).  The
     first call of a stage scores every staged long contig against the centroids in one
-    launch; the other calls are lookups."""
+    launch; the other calls are lookups.  The cache keeps the four dicts it was computed from
+    alive and compares them with ``is`` (an id() can be reused once its object is freed)."""
 
     def __init__(self):
-        self.key = None
-        self.result = {}
         import threading
         self.lock = threading.Lock()
+        self.reset()
+
+    def reset(self):
+        self.key = None
+        self.result = {}
+
+    def _same(self, key):
+        return (self.key is not None and all(a is b for a, b in zip(self.key[:4], key[:4]))
+                and self.key[4:] == key[4:])
 
     def lookup(self, contigid, coverages, profiles, bin_tetramer_profiles,
                bin_coverage_profiles):
-        key = (id(coverages), id(profiles), id(bin_tetramer_profiles),
-               id(bin_coverage_profiles), len(bin_tetramer_profiles), len(profiles))
+        key = (coverages, profiles, bin_tetramer_profiles, bin_coverage_profiles,
+               len(bin_tetramer_profiles), len(profiles))
         with self.lock:
-            if key != self.key or contigid not in self.result:
+            if not self._same(key) or contigid not in self.result:
                 order = list(bin_tetramer_profiles)
                 cen_prof = np.stack([np.asarray(bin_tetramer_profiles[b], dtype=np.float64)
                                      for b in order])
@@ -273,12 +303,13 @@ class _CentroidCache:
                     raise KeyError(contigid)
                 arg, w = _backend.backend().score_centroids(
                     profiles, coverages, np.asarray(queries, dtype=np.int64), cen_prof, cen_cov)
-                self.result = {c: (int(a), float(x)) for c, a, x in zip(queries, arg, w)}
+                self.result = dict(zip(queries, zip(arg.tolist(), w.tolist())))
                 self.key = key
             return self.result[contigid]
 
 
 _centroids = _CentroidCache()
+_backend._reset_hooks.append(_centroids.reset)
 
 
 def assign_long(contigid, coverages, normalized_tetramer_profiles, bin_tetramer_profiles,

@@ -156,8 +156,20 @@ class PeerExchange:
     instead of NCCL collectives: every rank owns one symmetric buffer (torch's symmetric-memory
     allocator: CUDA VMM handles exchanged at rendezvous, every peer's buffer mapped into every
     process) holding, per step parity, the gathered assignments of all ranks and the bin
-    tables.  ``push_*`` launch ``mcg_push_to_peers`` on the library's stream; ``barrier`` (the
-    allocation's signal pads, a few microseconds) tells everyone the blocks have landed.
+    tables.
+
+    Ordering rules (all enforced here, not left to the caller):
+      * ``push_*`` and ``barrier`` run on ONE stream: the ``stream`` argument, or torch's current
+        stream when it is None -- never the library's private stream, which nothing would order
+        against the signal.  ``barrier(stream=...)`` enters that stream before it signals.
+      * shards are ragged (``rows_per_rank`` may be a list: partition_by_bases gives every rank a
+        different row count); ``push_assignments`` checks the size of what it is given against
+        this rank's row count.
+      * a view returned by ``assignments(par)`` / ``centroids(par)`` is overwritten by the
+        peers' pushes of the NEXT use of that parity.  A reader on another stream must call
+        ``reader_done(par, stream)`` when its last read is queued; the next ``push_*`` of that
+        parity from THIS rank waits for it, and the peers' pushes are behind the barrier this
+        rank only passes after that wait (every exchange step ends with ``barrier``).
 
     Raises when symmetric memory cannot be set up (no peer access between the GPUs): callers
     fall back to ``broadcast_centroids`` / ``gather_assignments``.
@@ -167,12 +179,23 @@ class PeerExchange:
         import torch.distributed._symmetric_memory as symm
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
-        self.rows = int(rows_per_rank)
+        if isinstance(rows_per_rank, (int, np.integer)):
+            counts = [int(rows_per_rank)] * self.world
+        else:
+            counts = [int(c) for c in rows_per_rank]
+        if len(counts) != self.world or min(counts) < 0:
+            raise ValueError("rows_per_rank must give one row count per rank")
+        self.counts = counts
+        self.first = [0]
+        for c in counts:
+            self.first.append(self.first[-1] + c)
+        self.rows = counts[self.rank]
         self.n_bins, self.n_samples = int(n_bins), int(n_samples)
 
         def up(x):
             return (x + 255) // 256 * 256
-        total = self.world * self.rows
+        total = self.first[-1]
+        self.total = total
         self.off_arg = 0
         self.off_w = up(4 * total)
         self.off_prof = self.off_w + up(8 * total)
@@ -184,6 +207,7 @@ class PeerExchange:
         if len(self.ptrs) != self.world or not all(self.ptrs):
             raise RuntimeError("symmetric memory rendezvous gave no peer pointers")
         self.buf.zero_()
+        self._read = [None, None]
         torch.cuda.synchronize()
         self.handle.barrier(channel=0)
 
@@ -191,37 +215,65 @@ class PeerExchange:
         start = par * self.slot + off
         return self.buf[start:start + count * dtype.itemsize].view(dtype)
 
+    @staticmethod
+    def _stream(stream):
+        return stream if stream is not None else torch.cuda.current_stream()
+
     def assignments(self, par):
-        """(argmin int32[world * rows], wmin float64[world * rows]) of this rank's buffer."""
-        total = self.world * self.rows
-        return (self._view(par, self.off_arg, total, torch.int32),
-                self._view(par, self.off_w, total, torch.float64))
+        """(argmin int32[total rows], wmin float64[total rows]) of this rank's buffer, ranks in
+        order; valid until the next exchange of the same parity (see the class notes)."""
+        return (self._view(par, self.off_arg, self.total, torch.int32),
+                self._view(par, self.off_w, self.total, torch.float64))
 
     def centroids(self, par):
         return (self._view(par, self.off_prof, 136 * self.n_bins, torch.float64).view(self.n_bins, 136),
                 self._view(par, self.off_cov, self.n_samples * self.n_bins,
                            torch.float64).view(self.n_bins, self.n_samples))
 
+    def reader_done(self, par, stream=None):
+        """The last read of the parity-``par`` views is queued on ``stream``."""
+        ev = torch.cuda.Event()
+        ev.record(self._stream(stream))
+        self._read[par] = ev
+
+    def _before_push(self, par, st):
+        ev, self._read[par] = self._read[par], None
+        if ev is not None:
+            st.wait_event(ev)
+
     def push_assignments(self, ctx, par, d_argmin, d_wmin, stream=None):
-        """This rank's rows into everyone's gathered arrays (an all-gather by stores), on
-        ``stream`` (torch stream; default: the library's)."""
+        """This rank's rows into everyone's gathered arrays (an all-gather by stores)."""
+        if d_argmin.numel() != self.rows or d_wmin.numel() != self.rows:
+            raise ValueError("rank %d owns %d rows, got %d / %d" % (
+                self.rank, self.rows, d_argmin.numel(), d_wmin.numel()))
+        if d_argmin.dtype != torch.int32 or d_wmin.dtype != torch.float64:
+            raise ValueError("assignments must be int32 / float64")
+        st = self._stream(stream)
+        self._before_push(par, st)
+        if self.rows == 0:
+            return
         base = par * self.slot
-        st = stream.cuda_stream if stream is not None else None
+        mine = self.first[self.rank]
         ctx.push_to_peers(d_argmin.data_ptr(), 4 * self.rows,
-                          [p + base + self.off_arg + 4 * self.rank * self.rows for p in self.ptrs], st)
+                          [p + base + self.off_arg + 4 * mine for p in self.ptrs], st.cuda_stream)
         ctx.push_to_peers(d_wmin.data_ptr(), 8 * self.rows,
-                          [p + base + self.off_w + 8 * self.rank * self.rows for p in self.ptrs], st)
+                          [p + base + self.off_w + 8 * mine for p in self.ptrs], st.cuda_stream)
 
     def push_centroids(self, ctx, par, cen_prof, cen_cov, stream=None):
         """The source rank's bin tables into everyone's buffer (a broadcast by stores)."""
+        if cen_prof.numel() != 136 * self.n_bins or cen_cov.numel() != self.n_samples * self.n_bins:
+            raise ValueError("centroid tables must be [%d,136] and [%d,%d]" % (
+                self.n_bins, self.n_bins, self.n_samples))
+        st = self._stream(stream)
+        self._before_push(par, st)
         base = par * self.slot
-        st = stream.cuda_stream if stream is not None else None
         ctx.push_to_peers(cen_prof.data_ptr(), cen_prof.numel() * 8,
-                          [p + base + self.off_prof for p in self.ptrs], st)
+                          [p + base + self.off_prof for p in self.ptrs], st.cuda_stream)
         ctx.push_to_peers(cen_cov.data_ptr(), cen_cov.numel() * 8,
-                          [p + base + self.off_cov for p in self.ptrs], st)
+                          [p + base + self.off_cov for p in self.ptrs], st.cuda_stream)
 
-    def barrier(self, channel=0):
-        """All ranks meet on the CURRENT torch stream (everything pushed on it before has landed
-        everywhere when the barrier is passed)."""
-        self.handle.barrier(channel=channel)
+    def barrier(self, channel=0, stream=None):
+        """All ranks meet on ``stream`` (default: torch's current stream): everything pushed on
+        it before has landed everywhere when the barrier is passed."""
+        with torch.cuda.stream(self._stream(stream)):
+            self.handle.barrier(channel=channel)

@@ -35,7 +35,10 @@ class OracleBackend:
         self._have = have
         return prof, cov
 
-    def tetramer_scan(self, blob, offsets):
+    def reset(self):
+        pass
+
+    def tetramer_scan(self, blob, offsets, packed=None):
         counts, freqs = oracle.count_kmers_batch(blob, offsets)
         return counts.astype(np.uint32), freqs
 
@@ -50,6 +53,30 @@ class OracleBackend:
             if not self._have[c]:
                 raise KeyError(int(c))
         return oracle.score_members(prof, cov, queries, members, seg_offsets, rule)
+
+    def score_member_items(self, profiles, coverages, item_query, item_bin, members, seg_offsets,
+                           rule):
+        queries = sorted(set(int(q) for q in item_query))
+        row = {q: i for i, q in enumerate(queries)}
+        dense = self.score_members(profiles, coverages, np.asarray(queries, dtype=np.int64),
+                                   members, seg_offsets, rule)
+        return np.array([dense[row[int(q)], int(b)] for q, b in zip(item_query, item_bin)])
+
+    def frontier(self, indptr, indices, version, labels):
+        self._graph = (np.asarray(indptr), np.asarray(indices))
+        self._labels = np.array(labels, dtype=np.int32)
+
+    def frontier_patch(self, ids, bins):
+        for i, b in zip(ids, bins):
+            self._labels[int(i)] = int(b)
+
+    def frontier_walks(self, starts, depth_limit):
+        indptr, indices = self._graph
+        lists = [ref_bfs(int(s), depth_limit, self._labels, indptr, indices) for s in starts]
+        count = np.array([len(h) for h in lists], dtype=np.int32)
+        first = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64)
+        flat = [t for h in lists for t in h]
+        return first, count, np.array(flat, dtype=np.int32).reshape(-1, 3)
 
     def score_centroids(self, profiles, coverages, queries, cen_prof, cen_cov):
         prof, cov = self._tables(profiles, coverages)
