@@ -1641,8 +1641,9 @@ member_items_kernel(ScoreSide T, const int64_t *__restrict__ item_query,
         if (lane == 0) {
             double w;
             if (rule == MCG_RULE_A)
-                w = (sum != INFINITY && hi > lo) ? __ddiv_rn(sum, static_cast<double>(hi - lo))
-                                                 : MCG_MAX_WEIGHT;
+                // (an empty bin is 0 / 0 here as in aggregate_members_kernel; the reference
+                // raises ZeroDivisionError at matching_utils.py:152)
+                w = (sum != INFINITY) ? __ddiv_rn(sum, static_cast<double>(hi - lo)) : MCG_MAX_WEIGHT;
             else
                 w = (sum != INFINITY && n_valid != 0) ? __ddiv_rn(sum, static_cast<double>(n_valid))
                                                       : MCG_MAX_WEIGHT;

@@ -424,3 +424,135 @@ void orc_cov_terms(const double *cov, int64_t n, double *logc, double *lgam)
         lgam[i] = orc_lgamma(cov[i] + 1.0);
     }
 }
+
+/* ---- synthetic contigs: the generator of csrc/mcg_scan.cu (synth_kernel) restated ----------
+ * SURVEY.md section 8d workload.  bench.py --impl reference draws its bases with this function,
+ * so that the reference arm needs neither the CUDA library nor a GPU; tests check that the two
+ * generators write the same bytes.  Positions [p_begin, p_end) of the blob, whole 256-base
+ * chunks (p_begin a multiple of 256). */
+static uint64_t orc_splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+typedef struct {
+    const int64_t *offsets;
+    int64_t n_contigs;
+    const int32_t *genome_of;
+    const float *trans;
+    uint64_t seed;
+    float n_run_prob, lower_frac;
+    uint8_t *bases;
+    int64_t n_bases, chunk0;
+} orc_synth_t;
+
+static void orc_synth_body(int64_t i, void *p)
+{
+    orc_synth_t *a = (orc_synth_t *)p;
+    const int64_t chunk = a->chunk0 + i;
+    const int64_t p0 = chunk * 256;
+    if (p0 >= a->n_bases) return;
+    const int64_t p1 = p0 + 256 < a->n_bases ? p0 + 256 : a->n_bases;
+    int64_t lo = 0, hi = a->n_contigs;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a->offsets[mid] <= p0) lo = mid; else hi = mid;
+    }
+    int64_t c = lo, cend = a->offsets[c + 1];
+    const uint64_t key = orc_splitmix64(a->seed ^ ((uint64_t)chunk * 0xD6E8FEB86659FD93ull));
+    int n_lo = 1 << 30, n_hi = 0;
+    if ((float)(key & 0xFFFFFF) * (1.0f / 16777216.0f) < a->n_run_prob) {
+        n_lo = (int)((key >> 24) & 0xFF);
+        n_hi = n_lo + 1 + (int)((key >> 32) % 50);
+    }
+    static const char alphabet[4] = {'A', 'C', 'G', 'T'};
+    uint32_t prev = (uint32_t)(key >> 40) & 3u;
+    uint64_t bits = 0, ctr = 0;
+    int have = 0;
+    for (int64_t q = p0; q < p1; ++q) {
+        while (q >= cend) { ++c; cend = a->offsets[c + 1]; }
+        const int g = a->genome_of[c];
+        if (have == 0) { bits = orc_splitmix64(key + (++ctr)); have = 4; }
+        const float uni = (float)(bits & 0xFFFF) * (1.0f / 65536.0f);
+        bits >>= 16;
+        --have;
+        const float *t = a->trans + (g * 4 + prev) * 4;
+        uint32_t b = 3;
+        const float c0 = t[0], c1 = c0 + t[1], c2 = c1 + t[2];
+        if (uni < c0) b = 0; else if (uni < c1) b = 1; else if (uni < c2) b = 2;
+        prev = b;
+        uint8_t ch = (uint8_t)alphabet[b];
+        const int rel = (int)(q - p0);
+        if (rel >= n_lo && rel < n_hi) ch = 'N';
+        const uint64_t ck = orc_splitmix64(a->seed * 31ull + (uint64_t)c);
+        if ((float)(ck & 0xFFFFFF) * (1.0f / 16777216.0f) < a->lower_frac) ch |= 0x20;
+        a->bases[q] = ch;
+    }
+}
+
+void orc_synth_bases(const int64_t *offsets, int64_t n_contigs, const int32_t *genome_of,
+                     const float *trans, uint64_t seed, double n_frac, double lower_frac,
+                     uint8_t *bases, int64_t p_begin, int64_t p_end, int nthreads)
+{
+    orc_synth_t a;
+    a.offsets = offsets; a.n_contigs = n_contigs; a.genome_of = genome_of; a.trans = trans;
+    a.seed = seed;
+    a.n_run_prob = (float)(n_frac * 256.0 / 25.5);
+    a.lower_frac = (float)lower_frac;
+    a.bases = bases;
+    a.n_bases = p_end < offsets[n_contigs] ? p_end : offsets[n_contigs];
+    a.chunk0 = p_begin / 256;
+    const int64_t chunks = (a.n_bases + 255) / 256 - a.chunk0;
+    if (chunks > 0) orc_parallel_for(chunks, 64, nthreads, orc_synth_body, &a);
+}
+
+/* ---- bounded walk to labelled contigs: label_prop_utils.py:37-53, 92-100 restated ------------
+ * FIFO queue WITH duplicates (membership of the queue is not checked), depth[neighbour]
+ * overwritten on every sighting of an unvisited neighbour, labelled nodes (other than the
+ * start) reported at every pop and not expanded.  hits: (node, bin, depth) triples in pop
+ * order, at most max_hits of them written; returns the number of hits, -1 when out of memory.
+ * Pinned against tests/golden/score.npz (the reference's run_bfs_long) by
+ * tests/test_oracle_golden.py. */
+int64_t orc_bfs_long(const int64_t *indptr, const int32_t *indices, int64_t n_vertices,
+                     const int32_t *labels, int64_t start, int depth_limit, int32_t *hits,
+                     int64_t max_hits)
+{
+    int64_t cap = 1024, head = 0, tail = 0, n_hits = 0, n_visited = 0;
+    int32_t *queue = (int32_t *)malloc(sizeof(int32_t) * cap);
+    int32_t *depth = (int32_t *)malloc(sizeof(int32_t) * n_vertices);
+    uint8_t *visited = (uint8_t *)calloc(n_vertices, 1);
+    if (!queue || !depth || !visited) { free(queue); free(depth); free(visited); return -1; }
+    queue[tail++] = (int32_t)start;
+    depth[start] = 0;
+    while (head < tail) {
+        const int32_t v = queue[head++];
+        if (!visited[v]) { visited[v] = 1; ++n_visited; }
+        if (labels[v] >= 0 && n_visited > 1) {
+            if (n_hits < max_hits) {
+                hits[3 * n_hits] = v;
+                hits[3 * n_hits + 1] = labels[v];
+                hits[3 * n_hits + 2] = depth[v];
+            }
+            ++n_hits;
+            continue;
+        }
+        for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) {
+            const int32_t nb = indices[e];
+            if (visited[nb]) continue;
+            depth[nb] = depth[v] + 1;
+            if (depth[nb] > depth_limit) continue;
+            if (tail == cap) {
+                cap *= 2;
+                int32_t *grown = (int32_t *)realloc(queue, sizeof(int32_t) * cap);
+                if (!grown) { free(queue); free(depth); free(visited); return -1; }
+                queue = grown;
+            }
+            queue[tail++] = nb;
+        }
+    }
+    free(queue); free(depth); free(visited);
+    return n_hits;
+}

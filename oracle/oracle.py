@@ -69,6 +69,14 @@ def lib():
         L.orc_cov_terms.restype = None
         L.orc_cov_terms.argtypes = [_f64p, ctypes.c_int64, _f64p, _f64p]
         L.orc_max_threads.restype = ctypes.c_int
+        L.orc_synth_bases.restype = None
+        L.orc_synth_bases.argtypes = [_i64p, ctypes.c_int64, _i32p,
+                                      np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS"),
+                                      ctypes.c_uint64, ctypes.c_double, ctypes.c_double, _u8p,
+                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+        L.orc_bfs_long.restype = ctypes.c_int64
+        L.orc_bfs_long.argtypes = [_i64p, _i32p, ctypes.c_int64, _i32p, ctypes.c_int64,
+                                   ctypes.c_int, _i32p, ctypes.c_int64]
         _lib = L
     return _lib
 
@@ -183,3 +191,34 @@ def max_threads():
 def strip_ascii(raw):
     """str.strip() on bytes: what count_kmers does before scanning (feature_utils.py:63)."""
     return raw.decode("ascii").strip().encode("ascii")
+
+
+def synth_bases(offsets, genome_of, trans, seed, n_frac=1e-4, lower_frac=0.01, n_contigs=None,
+                nthreads=0):
+    """The synthetic contig generator of the CUDA library (mcg_synth_bases), restated: the
+    bases of the first ``n_contigs`` contigs (all by default), byte for byte."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    genome_of = np.ascontiguousarray(genome_of, dtype=np.int32)
+    trans = np.ascontiguousarray(trans, dtype=np.float32)
+    n = offsets.shape[0] - 1
+    end = int(offsets[n if n_contigs is None else n_contigs])
+    out = np.zeros(max(end, 1), dtype=np.uint8)
+    lib().orc_synth_bases(offsets, n, genome_of, trans, int(seed), float(n_frac), float(lower_frac),
+                          out, 0, end, nthreads)
+    return out[:end]
+
+
+def bfs_long(indptr, indices, labels, start, depth_limit, max_hits=4096):
+    """label_prop_utils.py:24-100 traversal: [(labelled node, bin, depth)] in pop order."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    while True:
+        hits = np.zeros((max_hits, 3), dtype=np.int32)
+        n = lib().orc_bfs_long(indptr, indices, indptr.shape[0] - 1, labels, int(start),
+                               int(depth_limit), hits.reshape(-1), max_hits)
+        if n < 0:
+            raise MemoryError("orc_bfs_long")
+        if n <= max_hits:
+            return [tuple(r) for r in hits[:n].tolist()]
+        max_hits = int(n)

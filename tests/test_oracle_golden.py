@@ -139,3 +139,36 @@ def test_cov_terms(score):
     flat = score["cov"].reshape(-1)
     assert np.array_equal(logc.reshape(-1), np.array([math.log(c) for c in flat]))
     assert np.array_equal(lgam.reshape(-1), np.array([math.lgamma(c + 1.0) for c in flat]))
+
+
+def test_bfs_long_matches_the_reference_walk(golden_dir):
+    """orc_bfs_long against run_bfs_long of the live reference (tests/golden/bfs.json, written by
+    tests/golden/make_bfs.py): the set of (labelled node, bin, depth) per start node and depth
+    limit, including the depths the overwrite behaviour (:93-98) produces."""
+    import json
+    from metacoag_b200 import synth
+    cases = json.load(open(os.path.join(golden_dir, "bfs.json")))
+    for name, case in cases.items():
+        indptr, indices = synth.csr_from_edges(case["n"], np.array(case["edges"]))
+        labels = np.array(case["labels"], dtype=np.int32)
+        for limit, per_start in case["expect"].items():
+            for s, want in zip(case["starts"], per_start):
+                got = oracle.bfs_long(indptr, indices, labels, s, int(limit))
+                assert sorted(set(got)) == [tuple(t) for t in want], (name, limit, s)
+
+
+def test_synth_generator_restated():
+    """orc_synth_bases draws the bytes of the library's generator (same splitmix64 streams);
+    here: determinism, alphabet and a prefix being independent of what follows it.  The
+    byte-for-byte comparison with mcg_synth_bases needs a GPU (tests/test_resident.py)."""
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(100, 5000, 50)
+    offsets = np.zeros(51, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    genome_of = rng.integers(0, 3, 50).astype(np.int32)
+    trans = rng.dirichlet(np.ones(4), size=12).astype(np.float32).reshape(3, 4, 4)
+    a = oracle.synth_bases(offsets, genome_of, trans, 7, n_frac=0.01, lower_frac=0.1)
+    b = oracle.synth_bases(offsets, genome_of, trans, 7, n_frac=0.01, lower_frac=0.1, n_contigs=20)
+    assert a.shape[0] == offsets[-1] and np.array_equal(a[:offsets[20]], b)
+    assert set(np.unique(a).tolist()) <= set(b"ACGTNacgtn")
+    assert (a == ord("N")).any() and (a >= ord("a")).any()
