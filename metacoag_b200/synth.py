@@ -176,3 +176,34 @@ def csr_from_edges(n, edges):
     np.cumsum(indptr, out=indptr)
     indices = both[:, 1].astype(np.int32) if both.shape[0] else np.zeros(0, dtype=np.int32)
     return indptr, indices
+
+
+def graph_csr_large(seed, genome_of, chord_frac=0.25, cross_frac=0.02):
+    """The graph recipe of ``_make_graph`` (per-genome chain + 0.25 n chords + 2 % cross-genome
+    edges) without Python loops, for the million-vertex benchmark configurations; returns the
+    simplified undirected CSR (indptr int64, indices int32, ascending neighbour ids)."""
+    rng = np.random.default_rng([seed, 4242])
+    genome_of = np.asarray(genome_of)
+    n = genome_of.shape[0]
+    # contigs of a genome in a random order, genomes one after the other
+    order = np.lexsort((rng.random(n), genome_of))
+    g_sorted = genome_of[order]
+    same = g_sorted[1:] == g_sorted[:-1]
+    chain = np.stack([order[:-1][same], order[1:][same]], axis=1)
+    # chords: a random partner inside the same genome's run of `order`
+    starts = np.flatnonzero(np.concatenate([[True], ~same]))
+    sizes = np.diff(np.concatenate([starts, [n]]))
+    run_of = np.repeat(np.arange(starts.shape[0]), sizes)
+    k = int(chord_frac * n)
+    a_pos = rng.integers(0, n, k)
+    b_pos = starts[run_of[a_pos]] + (rng.random(k) * sizes[run_of[a_pos]]).astype(np.int64)
+    chords = np.stack([order[a_pos], order[b_pos]], axis=1)
+    cross = rng.integers(0, n, (max(1, int(cross_frac * n)), 2))
+    edges = np.concatenate([chain, chords, cross]).astype(np.int64)
+    edges = edges[edges[:, 0] != edges[:, 1]]
+    both = np.concatenate([edges, edges[:, ::-1]])
+    key = np.unique(both[:, 0] * n + both[:, 1])
+    src, dst = key // n, key % n
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(src, minlength=n), out=indptr[1:])
+    return indptr, dst.astype(np.int32)
