@@ -154,6 +154,8 @@ extern "C" mcg_ctx *mcg_create(int device) {
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->copy2_done, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->cov_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->cov_ev, cudaEventDisableTiming);
     for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->copy_start, cudaEventDisableTiming);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i) cudaEventCreate(&ctx->ev[i]);
@@ -184,6 +186,8 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
     if (ctx->g_pinned) cudaFreeHost(ctx->g_pinned);
     if (ctx->pinned_pack) cudaFreeHost(ctx->pinned_pack);
     if (ctx->copy2_done) cudaEventDestroy(ctx->copy2_done);
+    if (ctx->cov_ev) cudaEventDestroy(ctx->cov_ev);
+    if (ctx->cov_stream) cudaStreamDestroy(ctx->cov_stream);
     if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
     for (int i = 0; i < 2 * MCG_N_TIMERS; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -726,18 +730,41 @@ extern "C" int mcg_set_profiles(mcg_ctx *ctx, const double *prof, int64_t n) {
 }
 
 // ---- coverage -----------------------------------------------------------------------------------------
-static int load_coverage_locked(mcg_ctx *ctx, const double *cov, int64_t n, int S) {
+// room for [n, S] coverages and their terms; `upload` = copy them now, on the compute stream
+static int load_coverage_locked(mcg_ctx *ctx, const double *cov, int64_t n, int S,
+                                bool upload = true) {
     if (n < 0 || S <= 0 || (n > 0 && !cov)) return mcg_fail(ctx, MCG_ERR_ARG, "bad coverage arguments");
     const size_t bytes = sizeof(double) * static_cast<size_t>(std::max<int64_t>(n, 1)) * S;
     MCG_TRY(mcg_reserve(ctx, ctx->cov, bytes));
     MCG_TRY(mcg_reserve(ctx, ctx->logc, bytes));
     MCG_TRY(mcg_reserve(ctx, ctx->lgam, bytes));
-    {
+    if (upload) {
         TimerScope t(ctx, T_H2D);
         MCG_TRY(h2d(ctx, ctx->cov.p, cov, sizeof(double) * n * S));
     }
     ctx->n_cov = n;
     ctx->n_samples = S;
+    return MCG_OK;
+}
+
+// Coverage rows [c0, c1) of a wave: copy and coverage terms on the side stream, so that they run
+// under the kernels of the waves in front; the compute stream waits for them where the wave's
+// scoring starts.  (The scans need no coverage: with the table sent up-front the first scan
+// waited for S x 8 bytes per contig -- 4 GB at 5 M contigs x 100 samples -- on the same link.)
+static int wave_coverage(mcg_ctx *ctx, const double *cov, int64_t c0, int64_t c1) {
+    const int S = ctx->n_samples;
+    const size_t off = static_cast<size_t>(c0) * S;
+    const int64_t count = (c1 - c0) * S;
+    MCG_CUDA(ctx, cudaMemcpyAsync(ctx->cov.as<double>() + off, cov + off, sizeof(double) * count,
+                                  cudaMemcpyHostToDevice, ctx->cov_stream));
+    cudaStream_t keep = ctx->stream;
+    ctx->stream = ctx->cov_stream;
+    const int rc = mcg_k_cov_terms(ctx, ctx->cov.as<double>() + off, ctx->logc.as<double>() + off,
+                                   ctx->lgam.as<double>() + off, count);
+    ctx->stream = keep;
+    MCG_TRY(rc);
+    MCG_CUDA(ctx, cudaEventRecord(ctx->cov_ev, ctx->cov_stream));
+    MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->cov_ev, 0));
     return MCG_OK;
 }
 
@@ -1515,14 +1542,18 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
     MCG_ENTER(ctx);
     if (n <= 0) return mcg_fail(ctx, MCG_ERR_ARG, "no contigs");
     MCG_MARK("enter");
-    MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples));
+    const bool waves = offsets && offsets[n] >= (64 << 20) && !getenv("MCG_NO_WAVES");
+    MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples, !waves));
     MCG_TRY(set_centroids_locked(ctx, cen_prof, cen_cov, n_bins, n_samples));
     MCG_MARK("cov+centroids queued");
-    if (offsets && offsets[n] >= (64 << 20) && !getenv("MCG_NO_WAVES")) {
+    if (waves) {
         // Large loads (ASCII or 2 bit): every contig range is scanned, normalised and scored as
         // soon as its packed words are complete in stream order, while the rest is still
         // uploading; after the last copy only the last range is left to do.
-        MCG_TRY(cov_terms_locked(ctx));
+        // the side stream starts behind whatever the compute stream still has queued (the last
+        // call's readers of the coverage tables)
+        MCG_CUDA(ctx, cudaEventRecord(ctx->copy_start, ctx->stream));
+        MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->cov_stream, ctx->copy_start, 0));
         MCG_TRY(mcg_reserve(ctx, ctx->counts, sizeof(uint32_t) * MCG_NPROF * n));
         MCG_TRY(mcg_reserve(ctx, ctx->prof, sizeof(double) * MCG_NPROF * n));
         MCG_TRY(mcg_reserve(ctx, ctx->prof_norm, sizeof(double) * n));
@@ -1532,7 +1563,7 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
         ctx->n_prof = n;
         const bool was_profiling = ctx->profiling;
         const WaveFactory factory = [&](const std::vector<ContigMeta> &meta, int64_t n_seg) -> WaveFn {
-            return [ctx, &meta, n_seg, n](int64_t c0, int64_t c1) -> int {
+            return [ctx, &meta, n_seg, n, cov](int64_t c0, int64_t c1) -> int {
                 if (c1 <= c0) return MCG_OK;
                 const bool prof = ctx->profiling;
                 ctx->profiling = false;   // one event pair per timer: the waves share T_H2D
@@ -1546,6 +1577,10 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
                                                ctx->meta.as<ContigMeta>() + c0, c1 - c0,
                                                ctx->prof.as<double>() + c0 * MCG_NPROF,
                                                ctx->prof_norm.as<double>() + c0);
+                // coverage rows of the range: queued on the side stream now (they travel and are
+                // featurised under the kernels of the waves in front); the compute stream waits
+                // for them here, behind this range's scan
+                if (rc == MCG_OK) rc = wave_coverage(ctx, cov, c0, c1);
                 if (rc == MCG_OK) {
                     ScoreSide a = contig_side(ctx, nullptr, c1 - c0);
                     a.first = c0;

@@ -40,6 +40,8 @@ struct mcg_ctx {
     cudaStream_t copy_stream = nullptr;   // H2D of contig chunks, overlapped with packing
     cudaStream_t copy_stream2 = nullptr;  // H2D of host-packed chunks
     cudaEvent_t copy2_done = nullptr;
+    cudaStream_t cov_stream = nullptr;    // coverage rows of a wave: H2D + coverage terms
+    cudaEvent_t cov_ev = nullptr;
     void *pinned_pack = nullptr;          // host-packed contigs, staged for the copy engine
     size_t pinned_pack_cap = 0;
     int reserved_sms = 0;                 // SMs the persistent scan leaves free (mcg_set_reserved_sms)

@@ -516,15 +516,15 @@ void orc_synth_bases(const int64_t *offsets, int64_t n_contigs, const int32_t *g
  * order, at most max_hits of them written; returns the number of hits, -1 when out of memory.
  * Pinned against tests/golden/score.npz (the reference's run_bfs_long) by
  * tests/test_oracle_golden.py. */
-int64_t orc_bfs_long(const int64_t *indptr, const int32_t *indices, int64_t n_vertices,
-                     const int32_t *labels, int64_t start, int depth_limit, int32_t *hits,
-                     int64_t max_hits)
+/* scratch: depth int32[n_vertices] (any content), visited uint8[n_vertices] (all zero on entry
+ * and on return: only the touched entries are cleared), so a batch of walks costs its walks */
+static int64_t orc_bfs_long_scratch(const int64_t *indptr, const int32_t *indices,
+                                    const int32_t *labels, int64_t start, int depth_limit,
+                                    int32_t *hits, int64_t max_hits, int32_t *depth, uint8_t *visited)
 {
     int64_t cap = 1024, head = 0, tail = 0, n_hits = 0, n_visited = 0;
     int32_t *queue = (int32_t *)malloc(sizeof(int32_t) * cap);
-    int32_t *depth = (int32_t *)malloc(sizeof(int32_t) * n_vertices);
-    uint8_t *visited = (uint8_t *)calloc(n_vertices, 1);
-    if (!queue || !depth || !visited) { free(queue); free(depth); free(visited); return -1; }
+    if (!queue) return -1;
     queue[tail++] = (int32_t)start;
     depth[start] = 0;
     while (head < tail) {
@@ -547,12 +547,46 @@ int64_t orc_bfs_long(const int64_t *indptr, const int32_t *indices, int64_t n_ve
             if (tail == cap) {
                 cap *= 2;
                 int32_t *grown = (int32_t *)realloc(queue, sizeof(int32_t) * cap);
-                if (!grown) { free(queue); free(depth); free(visited); return -1; }
+                if (!grown) { free(queue); return -1; }
                 queue = grown;
             }
             queue[tail++] = nb;
         }
     }
-    free(queue); free(depth); free(visited);
+    for (int64_t i = 0; i < tail; ++i) visited[queue[i]] = 0;   /* every visited vertex was queued */
+    free(queue);
     return n_hits;
+}
+
+int64_t orc_bfs_long(const int64_t *indptr, const int32_t *indices, int64_t n_vertices,
+                     const int32_t *labels, int64_t start, int depth_limit, int32_t *hits,
+                     int64_t max_hits)
+{
+    int32_t *depth = (int32_t *)malloc(sizeof(int32_t) * n_vertices);
+    uint8_t *visited = (uint8_t *)calloc(n_vertices, 1);
+    int64_t n = -1;
+    if (depth && visited)
+        n = orc_bfs_long_scratch(indptr, indices, labels, start, depth_limit, hits, max_hits, depth,
+                                 visited);
+    free(depth); free(visited);
+    return n;
+}
+
+/* A batch of walks, one after the other on one thread with shared scratch (what a C port of the
+ * reference's loop over start nodes costs): hit_count[i] hits of start i, the first max_hits of
+ * each in hits[i * 3 * max_hits ...].  Returns 0, -1 when out of memory. */
+int orc_bfs_long_batch(const int64_t *indptr, const int32_t *indices, int64_t n_vertices,
+                       const int32_t *labels, const int64_t *starts, int64_t n_starts,
+                       int depth_limit, int32_t *hits, int64_t max_hits, int64_t *hit_count)
+{
+    int32_t *depth = (int32_t *)malloc(sizeof(int32_t) * n_vertices);
+    uint8_t *visited = (uint8_t *)calloc(n_vertices, 1);
+    int rc = (depth && visited) ? 0 : -1;
+    for (int64_t i = 0; rc == 0 && i < n_starts; ++i) {
+        hit_count[i] = orc_bfs_long_scratch(indptr, indices, labels, starts[i], depth_limit,
+                                            hits + 3 * max_hits * i, max_hits, depth, visited);
+        if (hit_count[i] < 0) rc = -1;
+    }
+    free(depth); free(visited);
+    return rc;
 }

@@ -77,6 +77,9 @@ def lib():
         L.orc_bfs_long.restype = ctypes.c_int64
         L.orc_bfs_long.argtypes = [_i64p, _i32p, ctypes.c_int64, _i32p, ctypes.c_int64,
                                    ctypes.c_int, _i32p, ctypes.c_int64]
+        L.orc_bfs_long_batch.restype = ctypes.c_int
+        L.orc_bfs_long_batch.argtypes = [_i64p, _i32p, ctypes.c_int64, _i32p, _i64p, ctypes.c_int64,
+                                         ctypes.c_int, _i32p, ctypes.c_int64, _i64p]
         _lib = L
     return _lib
 
@@ -222,3 +225,26 @@ def bfs_long(indptr, indices, labels, start, depth_limit, max_hits=4096):
         if n <= max_hits:
             return [tuple(r) for r in hits[:n].tolist()]
         max_hits = int(n)
+
+
+def bfs_long_batch(indptr, indices, labels, starts, depth_limit, max_hits=64):
+    """The walks of ``bfs_long`` for many start nodes on one thread with shared scratch: a list of
+    hit lists.  Walks with more than ``max_hits`` hits are repeated one by one."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    n = starts.shape[0]
+    hits = np.zeros((n, max_hits, 3), dtype=np.int32)
+    count = np.zeros(n, dtype=np.int64)
+    rc = lib().orc_bfs_long_batch(indptr, indices, indptr.shape[0] - 1, labels, starts, n,
+                                  int(depth_limit), hits.reshape(-1), max_hits, count)
+    if rc != 0:
+        raise MemoryError("orc_bfs_long_batch")
+    out = []
+    for i in range(n):
+        if count[i] <= max_hits:
+            out.append([tuple(r) for r in hits[i, :count[i]].tolist()])
+        else:
+            out.append(bfs_long(indptr, indices, labels, int(starts[i]), depth_limit, int(count[i])))
+    return out
