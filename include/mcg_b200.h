@@ -19,6 +19,8 @@
  *     behind one caller) and is internally mutex-guarded
  *     (label_prop_utils.assign_long is entered from several Python threads,
  *     metacoag:959-999, and ctypes drops the GIL);
+ *   - a call makes the context's device current for its duration and puts the caller's
+ *     current device back before it returns;
  *   - there is no CPU fallback: without a CUDA device mcg_create() fails.
  */
 #ifndef MCG_B200_H

@@ -106,10 +106,20 @@ static int sync(mcg_ctx *ctx) {
     return MCG_OK;
 }
 
+// Serialises the calls of a context and makes its device current for the call; the caller's
+// current device is put back on return (a pool talks to several devices from one thread, and a
+// host program -- torch, for one -- keeps its own notion of the current device).
 struct Guard {
     mcg_ctx *ctx;
     std::unique_lock<std::mutex> lock;
-    explicit Guard(mcg_ctx *c) : ctx(c), lock(c->mu) { cudaSetDevice(c->device); }
+    int prev = -1;
+    explicit Guard(mcg_ctx *c) : ctx(c), lock(c->mu) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != c->device) cudaSetDevice(c->device);
+    }
+    ~Guard() {
+        if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    }
 };
 
 #define MCG_ENTER(ctx)                                   \
@@ -136,10 +146,16 @@ extern "C" mcg_ctx *mcg_create(int device) {
         mcg_set_global_error("device index out of range");
         return nullptr;
     }
+    int prev_device = -1;
+    if (cudaGetDevice(&prev_device) != cudaSuccess) prev_device = -1;
     if (cudaSetDevice(device) != cudaSuccess) {
         mcg_set_global_error("cudaSetDevice failed");
         return nullptr;
     }
+    struct Restore {
+        int prev, cur;
+        ~Restore() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
+    } restore{prev_device, device};
     mcg_ctx *ctx = new mcg_ctx();
     ctx->device = device;
     if (const char *env = getenv("MCG_PRUNE")) ctx->prune = atoi(env) != 0;
@@ -170,6 +186,12 @@ extern "C" mcg_ctx *mcg_create(int device) {
 
 extern "C" void mcg_destroy(mcg_ctx *ctx) {
     if (!ctx) return;
+    int prev_device = -1;
+    if (cudaGetDevice(&prev_device) != cudaSuccess) prev_device = -1;
+    struct Restore {
+        int prev, cur;
+        ~Restore() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
+    } restore{prev_device, ctx->device};
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->packed, &ctx->meta, &ctx->seg_contig, &ctx->ascii, &ctx->offsets,
