@@ -106,6 +106,17 @@ int mcg_set_host_pack_threads(mcg_ctx *ctx, int threads);
  * (label_prop_utils.py:340-345, first minimum) are the same bits with and without.  On by
  * default; 0 scores every pair (measurement, tests). */
 int mcg_set_prune(mcg_ctx *ctx, int enabled);
+/* The distances the branch and bound rules bins out with come from the 5th-generation tensor
+ * cores (tcgen05.mma on an fp16 hi/lo split of the centred profiles, fp32 accumulators in tensor
+ * memory, operands by TMA; csrc/mcg_tc.cu) together with a rigorous error margin; every pair
+ * that is not ruled out gets its float64 distance (matching_utils.py:28-29) again, so results
+ * keep their bits.  On by default; 0 = the float64 distance matrix of round 1 (DMMA) for all
+ * pairs (measurement, tests). */
+int mcg_set_tc(mcg_ctx *ctx, int enabled);
+/* Parity / diagnostic form of that bound: d2a [nq, n_bins] fp32 against the resident centroids
+ * (mcg_set_centroids / mcg_bin_profiles) and margin [nq]: |d2a - d^2| <= margin[q] for every bin,
+ * d^2 the float64 squared tetramer distance.  queries NULL = rows 0..nq-1. */
+int mcg_tc_distances(mcg_ctx *ctx, const int64_t *queries, int64_t nq, float *d2a, float *margin);
 /* The scan kernel is persistent, one CTA per SM, and its shared memory leaves no room for
  * another kernel's CTA: a collective launched on another stream (the NCCL broadcast of the bin
  * tables, the all-gather of the assignments) would start only when the scan ends.  This keeps

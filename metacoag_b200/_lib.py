@@ -81,6 +81,8 @@ SIGNATURES = {
     "mcg_fasta_load": (_int, [_c.c_char_p, _vp, _vp, _vp, _vp, _i64, _i64, _i64]),
     "mcg_write_bin_fastas": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _c.c_int32]),
     "mcg_pack_2bit_host_mt": (_int, [_vp, _vp, _i64, _vp, _int]),
+    "mcg_set_tc": (_int, [_vp, _int]),
+    "mcg_tc_distances": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "mcg_score_member_items": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp]),
     "mcg_graph_load": (_int, [_vp, _vp, _vp, _i64]),
     "mcg_labels_load": (_int, [_vp, _vp, _i64]),
@@ -297,6 +299,22 @@ class Context:
     def set_prune(self, enabled):
         """Rule-C branch and bound on / off (include/mcg_b200.h); results do not change."""
         self._check(self.lib.mcg_set_prune(self.handle, int(bool(enabled))))
+
+    def set_tc(self, enabled):
+        """Tensor-core distance bound of the rule-C branch and bound on / off; results do not
+        change."""
+        self._check(self.lib.mcg_set_tc(self.handle, int(bool(enabled))))
+
+    def tc_distances(self, queries=None, nq=None):
+        """(d2a float32 [nq, n_bins], margin float32 [nq]) of the tensor-core distance bound
+        against the resident centroids."""
+        if queries is not None:
+            queries = _arr(queries, np.int64)
+            nq = queries.shape[0]
+        d2a = np.zeros((nq, self.n_bins), dtype=np.float32)
+        margin = np.zeros(nq, dtype=np.float32)
+        self._check(self.lib.mcg_tc_distances(self.handle, _ptr(queries), nq, _ptr(d2a), _ptr(margin)))
+        return d2a, margin
 
     def set_reserved_sms(self, sms):
         """SMs the persistent scan kernel leaves free for collectives on another stream."""

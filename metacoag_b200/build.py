@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcg_b200.so")
-SOURCES = ["mcg_api.cu", "mcg_scan.cu", "mcg_score.cu", "mcg_frontier.cu", "mcg_pool.cu"]
+SOURCES = ["mcg_api.cu", "mcg_scan.cu", "mcg_score.cu", "mcg_frontier.cu", "mcg_pool.cu", "mcg_tc.cu"]
 HOST_SOURCES = ["mcg_hostpack.cpp"]
 HEADERS = [os.path.join(CSRC, "mcg_internal.cuh"), os.path.join(ROOT, "include", "mcg_b200.h")]
 NVCC_FLAGS = [

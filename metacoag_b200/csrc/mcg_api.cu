@@ -199,7 +199,8 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
                       &ctx->lgam, &ctx->cen_prof, &ctx->cen_cov, &ctx->cen_logc, &ctx->cen_lgam,
                       &ctx->argmin, &ctx->wmin, &ctx->status, &ctx->prof_norm, &ctx->cen_norm,
                       &ctx->g_indptr, &ctx->g_indices, &ctx->g_labels, &ctx->g_work, &ctx->g_block,
-                      &ctx->g_starts, &ctx->g_patch};
+                      &ctx->g_starts, &ctx->g_patch, &ctx->tc_a, &ctx->tc_b, &ctx->tc_aaux,
+                      &ctx->tc_baux};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->scratch)
@@ -1798,6 +1799,50 @@ extern "C" int mcg_set_prune(mcg_ctx *ctx, int enabled) {
     MCG_ENTER(ctx);
     ctx->prune = enabled ? 1 : 0;
     return MCG_OK;
+}
+
+extern "C" int mcg_set_tc(mcg_ctx *ctx, int enabled) {
+    MCG_ENTER(ctx);
+    ctx->tc = enabled ? 1 : 0;
+    return MCG_OK;
+}
+
+// Diagnostic / parity form of the tensor-core distance bound: d2a [nq, n_bins] (fp32) of the
+// queries against the resident centroids and the margin [nq] within which every d2a is
+// guaranteed to lie around the float64 squared distance.
+extern "C" int mcg_tc_distances(mcg_ctx *ctx, const int64_t *queries, int64_t nq, float *d2a,
+                                float *margin) {
+    MCG_ENTER(ctx);
+    MCG_TRY(need_features(ctx));
+    if (ctx->n_bins == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no centroids resident");
+    if (nq < 0 || (nq > 0 && (!d2a || !margin))) return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
+    if (nq == 0) return MCG_OK;
+    const int64_t *d_queries = nullptr;
+    if (queries) {
+        MCG_TRY(check_ids(ctx, queries, nq, ctx->n_prof, "queries"));
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], sizeof(int64_t) * nq));
+        MCG_TRY(h2d(ctx, ctx->scratch[0].p, queries, sizeof(int64_t) * nq));
+        d_queries = ctx->scratch[0].as<int64_t>();
+    } else if (nq > ctx->n_prof) {
+        return mcg_fail(ctx, MCG_ERR_ARG, "nq exceeds the resident contig table");
+    }
+    const int64_t B = ctx->n_bins;
+    const long long ldf = mcg_tc_ldf(B);
+    const long long rows_pad = (nq + 127) / 128 * 128;
+    ctx->cand_valid = false;
+    ctx->redo_valid = false;
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[5], sizeof(float) * rows_pad * ldf));
+    MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(float) * nq));
+    MCG_TRY(mcg_k_tc_prep_bins(ctx, centroid_side(ctx)));
+    {
+        TimerScope t(ctx, T_DIST);
+        MCG_TRY(mcg_k_tc_dist(ctx, contig_side(ctx, d_queries, nq), B, ctx->scratch[5].as<float>(), ldf,
+                              ctx->scratch[1].as<float>(), nullptr, 0));
+    }
+    MCG_CUDA(ctx, cudaMemcpy2DAsync(d2a, sizeof(float) * B, ctx->scratch[5].p, sizeof(float) * ldf,
+                                    sizeof(float) * B, nq, cudaMemcpyDeviceToHost, ctx->stream));
+    MCG_TRY(d2h(ctx, margin, ctx->scratch[1].p, sizeof(float) * nq));
+    return sync(ctx);
 }
 
 extern "C" int mcg_prune_stats(mcg_ctx *ctx, int64_t stats[4]) {

@@ -90,6 +90,11 @@ struct mcg_ctx {
     void *g_pinned = nullptr;     // pinned mirror of the head of g_block
     size_t g_pinned_cap = 0;
 
+    // ---- tensor-core bound (mcg_tc.cu): fp16 operands and their norms ----------------
+    DevBuf tc_a, tc_b;            // __half [rows,448]
+    DevBuf tc_aaux, tc_baux;      // float: |x|^2, |x| per row (+ max |x_v| behind the bins)
+    int tc = 1;                   // rule-C branch and bound takes its distances from tcgen05 (mcg_set_tc)
+
     // ---- results / scratch ---------------------------------------------------------
     DevBuf argmin, wmin;       // int32 [n], f64 [n]
     DevBuf status;             // int32 [4] device-side flags (0: domain error)
@@ -213,6 +218,12 @@ int mcg_k_cov_prob(mcg_ctx *ctx, const double *d_c1, const double *d_c2, int64_t
                    double *d_out);
 int mcg_k_fp64_peak(mcg_ctx *ctx, double *tflops);
 int mcg_k_prune_stats(mcg_ctx *ctx, int64_t stats[4]);
+
+// mcg_tc.cu
+long long mcg_tc_ldf(long long bins);
+int mcg_k_tc_prep_bins(mcg_ctx *ctx, const ScoreSide &b);
+int mcg_k_tc_dist(mcg_ctx *ctx, const ScoreSide &a, long long bins, float *d_d2a, long long ldf,
+                  float *d_mrow, unsigned long long *d_tilemin, long long nbt64);
 
 // mcg_frontier.cu
 int mcg_k_bfs(mcg_ctx *ctx, const int64_t *d_indptr, const int32_t *d_indices, int64_t n_vertices,
