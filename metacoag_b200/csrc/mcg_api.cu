@@ -159,6 +159,7 @@ extern "C" mcg_ctx *mcg_create(int device) {
     mcg_ctx *ctx = new mcg_ctx();
     ctx->device = device;
     if (const char *env = getenv("MCG_PRUNE")) ctx->prune = atoi(env) != 0;
+    if (const char *env = getenv("MCG_TC")) ctx->tc = atoi(env) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -200,7 +201,7 @@ extern "C" void mcg_destroy(mcg_ctx *ctx) {
                       &ctx->argmin, &ctx->wmin, &ctx->status, &ctx->prof_norm, &ctx->cen_norm,
                       &ctx->g_indptr, &ctx->g_indices, &ctx->g_labels, &ctx->g_work, &ctx->g_block,
                       &ctx->g_starts, &ctx->g_patch, &ctx->tc_a, &ctx->tc_b, &ctx->tc_aaux,
-                      &ctx->tc_baux};
+                      &ctx->tc_baux, &ctx->tc_d2a, &ctx->tc_mrow};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->scratch)

@@ -93,6 +93,7 @@ struct mcg_ctx {
     // ---- tensor-core bound (mcg_tc.cu): fp16 operands and their norms ----------------
     DevBuf tc_a, tc_b;            // __half [rows,448]
     DevBuf tc_aaux, tc_baux;      // float: |x|^2, |x| per row (+ max |x_v| behind the bins)
+    DevBuf tc_d2a, tc_mrow;       // float [rows, ldf] approximate d^2 of a rule-C chunk, margin [rows]
     int tc = 1;                   // rule-C branch and bound takes its distances from tcgen05 (mcg_set_tc)
 
     // ---- results / scratch ---------------------------------------------------------

@@ -808,7 +808,11 @@ pair_kernel(ScoreSide A, ScoreSide B, int S, ScoreOut out, int32_t *__restrict__
 template <int DUMMY>
 __global__ void __launch_bounds__(kPairThreads, 3)
 dist2_kernel(ScoreSide A, ScoreSide B, double *__restrict__ d2out, long long ldc,
-             unsigned long long *__restrict__ tilemin, long long n_btiles_all) {
+             unsigned long long *__restrict__ tilemin, long long n_btiles_all,
+             const int *__restrict__ gate_total, int gate_cap) {
+    // behind the tensor-core bound this kernel only runs when the candidate list overflowed and
+    // prob_kernel has to score every pair after all
+    if (gate_total && *gate_total <= gate_cap) return;
     extern __shared__ __align__(16) double sm[];
     double *stage = sm;                                   // [2 stages][A, B][64][pitch]
     double *NA = stage + 4 * kChunkDoubles;
@@ -1207,9 +1211,16 @@ __global__ void bin_head_kernel(ScoreSide B, int S, int nq, long long ldh,
     head[(2 * q + 1) * ldh + j] = B.logc[brow * S + q];
 }
 
+// D2T = double: d2 is dist2_kernel's exact matrix (mrow = nullptr).  D2T = float: d2 is the
+// tensor-core estimate d2a of mcg_tc.cu and mrow[r] the margin within which every d2a of row r
+// lies around the true d^2.  Every use of a distance below is one-sided, so it takes the side of
+// the interval that keeps the bound valid: ruling a bin OUT compares the LOWER end
+// (d2a - margin), and the weight W of a probed bin -- which only has to be AT LEAST the weight
+// of some bin -- is evaluated at the UPPER end (the weight grows with the distance).
+template <typename D2T>
 __global__ void __launch_bounds__(256)
-bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
-             const double *__restrict__ head, long long ldh,
+bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long long ldc,
+             const float *__restrict__ mrow, const double *__restrict__ head, long long ldh,
              const unsigned long long *__restrict__ tilemin, CandList cl,
              int32_t *__restrict__ status) {
     __shared__ double ET[16];
@@ -1225,7 +1236,8 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
     const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
     for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wid; r < A.n;
          r += n_warps) {
-        const double *row = d2 + r * ldc;
+        const D2T *row = d2 + r * ldc;
+        const double mg = mrow ? static_cast<double>(mrow[r]) : 0.0;
         // dist2_kernel left the smallest d^2 of the row in every 64-bin tile (ordered bits):
         // lane t holds tile t; tiles whose minimum is beyond a threshold are never read
         const int nb = static_cast<int>(B.n);
@@ -1248,7 +1260,7 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
         for (int h = 0; h < 2; ++h) {
             const int j = 64 * bt_near + 32 * h + lane;
             if (j < nb) {
-                const double v = row[j];
+                const double v = static_cast<double>(row[j]);
                 if (v < dm) { dm = v; jm = j; }
             }
         }
@@ -1301,7 +1313,7 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
             const double lpc = log_comp_prob_warp(dd, ET, LT, status);
             return -(lpc + sl + (s1 < s2 ? s1 : s2)) * c_math.inv_ln10;
         };
-        double w = probe(jm, dm);
+        double w = probe(jm, dm + mg);
         // parabola(d) > W ln 10 + U  <=>  d > (-qb + sqrt(qb^2 + 4 qa target)) / (2 qa)
         auto threshold = [&](double wv) -> double {
             const double target = wv * (1.0 + 1e-9) * c_gauss.ln10 + cov_upper - c_math.prune_c;
@@ -1324,7 +1336,7 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
             for (int sb = 2 * (__ffs(tm) - 1), h = 0; h < 2 && sb < n_slabs; ++h, ++sb) {
                 const int j = 32 * sb + lane;
                 if (j < B.n) {
-                    const double dd = row[j];
+                    const double dd = fmax(static_cast<double>(row[j]) - mg, 0.0);
                     double e1 = 0.0;
                     const double *hp = head + j;
                     for (int q = 0; q < nq; ++q)
@@ -1341,7 +1353,7 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
                 if (ol < lb || (ol == lb && oj < jb)) { lb = ol; jb = oj; }
             }
             if (lb < INFINITY && jb != jm) {
-                const double w2 = probe(jb, row[jb]);
+                const double w2 = probe(jb, static_cast<double>(row[jb]) + mg);
                 if (w2 < w || !(w == w)) w = w2;
                 if (w < kPruneMaxWeight) thr2 = threshold(w);
             }
@@ -1359,12 +1371,13 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, lon
         for (unsigned tm = tiles; tm; tm &= tm - 1)   // the other tiles: every bin beyond thr2
         for (int sb = 2 * (__ffs(tm) - 1), h = 0; h < 2 && sb < n_slabs; ++h, ++sb) {
             const int j = 32 * sb + lane;
-            const double dd = j < nb ? row[j] : INFINITY;
+            const double raw = j < nb ? static_cast<double>(row[j]) : INFINITY;
+            const double dd = fmax(raw - mg, 0.0);       // lower end (a NaN stays in: dd = 0)
             bool keep = j < nb && !(dd > thr2);
             // prob_comp is exactly 0 from d = 0.2003 on (exp underflow, log_comp_prob_special):
             // the weight is MAX_WEIGHT, which never wins and means None when nothing else is
             // left.  Beyond d^2 = 1.5 the reference's own sequence decides (domain errors): kept.
-            if (dd > 0.0405 && dd < 1.5) keep = false;
+            if (dd > 0.0405 && raw + mg < 1.5) keep = false;
             if (slack < INFINITY && __any_sync(0xffffffffu, keep)) {
                 double e1 = 0.0;
                 const double *hp = head + (j < B.n ? j : 0);
@@ -1411,7 +1424,31 @@ __device__ __forceinline__ void ld_v4(double (&v)[4], const double *p) {
 // One thread per listed pair: the weight prob_kernel computes for it, operation for operation
 // (log_comp_prob_warp, excess sums in sample order, the e^-744 / e^-746 window, the GUARD
 // deferral); NaN marks a deferred pair.
-template <bool GUARD>
+// The float64 d^2 of one pair with the bits dist2_kernel gives it: mma.sync.m8n8k4.f64 is a chain
+// of FMAs over k in ascending order (experiments/dmma_fma_chain.cu: 262 144 of 262 144 outputs
+// bit-equal on the B200), the norms are the DMMA norms of row_norms_kernel, and the epilogue is
+// dist2_kernel's fma(-2, u.v, |u|^2 + |v|^2) clamped at 0.
+__device__ __forceinline__ double exact_d2(const ScoreSide &A, const ScoreSide &B, long long arow,
+                                           long long brow) {
+    const double *u = A.prof + arow * MCG_NPROF, *v = B.prof + brow * MCG_NPROF;
+    double acc = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < MCG_NPROF; k += 4) {   // rows are 32-byte aligned (136 x 8 = 34 x 32)
+        double a[4], b[4];
+        ld_v4(a, u + k);
+        ld_v4(b, v + k);
+        acc = fma(a[0], b[0], acc);
+        acc = fma(a[1], b[1], acc);
+        acc = fma(a[2], b[2], acc);
+        acc = fma(a[3], b[3], acc);
+    }
+    const double d2 = fma(-2.0, acc, A.norm[arow] + B.norm[brow]);
+    return d2 > 0.0 ? d2 : 0.0;
+}
+
+// EXACT: d2 is nullptr (the distances came from the tensor-core bound) and every listed pair gets
+// its float64 d^2 here.
+template <bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(256)
 cand_score_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2, long long ldc,
                   CandList cl, int32_t *__restrict__ status) {
@@ -1428,13 +1465,13 @@ cand_score_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2
     for (int i = blockIdx.x * blockDim.x + tid; i < padded; i += stride) {
         const bool live = i < total;
         const int2 pr = live ? cl.pair[i] : make_int2(0, 0);
-        const double dd = d2[pr.x * ldc + pr.y];
+        const long long arow = A.index ? A.index[A.first + pr.x] : (A.first + pr.x);
+        const long long brow = B.index ? B.index[B.first + pr.y] : (B.first + pr.y);
+        const double dd = EXACT ? exact_d2(A, B, arow, brow) : d2[pr.x * ldc + pr.y];
         const double log_pc = log_comp_prob_warp(dd, ET, LT, status);
         double tsum = log_pc;
         bool defer = false;
         if (log_pc == log_pc) {
-            const long long arow = A.index ? A.index[A.first + pr.x] : (A.first + pr.x);
-            const long long brow = B.index ? B.index[B.first + pr.y] : (B.first + pr.y);
             const double *ac_p = A.cov + arow * S, *al_p = A.logc + arow * S, *ag_p = A.lgam + arow * S;
             const double *bc_p = B.cov + brow * S, *bl_p = B.logc + brow * S, *bg_p = B.lgam + brow * S;
             double s1 = 0.0, s2 = 0.0;
@@ -1938,6 +1975,18 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
             b, S, nq, ldc, ctx->scratch[1].as<double>());
         MCG_KERNEL_CHECK(ctx);
     }
+    // distances for the bound: the tensor-core estimate (default) or dist2_kernel's exact matrix
+    const bool use_tc = use_cand && ctx->tc;
+    const long long ldf = mcg_tc_ldf(b.n);
+    float *d2a = nullptr, *mrow = nullptr;
+    if (use_tc) {
+        const long long rows_pad = (need_rows + 127) / 128 * 128;
+        MCG_TRY(mcg_reserve(ctx, ctx->tc_d2a, sizeof(float) * rows_pad * ldf));
+        MCG_TRY(mcg_reserve(ctx, ctx->tc_mrow, sizeof(float) * need_rows));
+        d2a = ctx->tc_d2a.as<float>();
+        mrow = ctx->tc_mrow.as<float>();
+        MCG_TRY(mcg_k_tc_prep_bins(ctx, b));
+    }
     const CandGate gate = {cl.total, cl.cap};
     ScoreOut shifted = out;   // outputs are indexed by (first + r): shift them back
     shifted.argmin = out.argmin - a.first;
@@ -1957,13 +2006,18 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         if (gy < 1) gy = 1;
         dim3 grid(static_cast<unsigned>(a_tiles), static_cast<unsigned>(gy), 1);
         mcg_timer_begin(ctx, T_DIST);
-        if (tilemin)   // 0x7f7f...: a finite number above every d^2
-            MCG_CUDA(ctx, cudaMemsetAsync(tilemin, 0x7f, sizeof(unsigned long long) * need_rows * b_tiles,
-                                          ctx->stream));
-        dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc, tilemin,
-                                                                       b_tiles);
+        if (use_tc) {
+            MCG_TRY(mcg_k_tc_dist(ctx, ac, b.n, d2a, ldf, mrow, tilemin, b_tiles));
+        } else {
+            if (tilemin)   // 0x7f7f...: a finite number above every d^2
+                MCG_CUDA(ctx, cudaMemsetAsync(tilemin, 0x7f,
+                                              sizeof(unsigned long long) * need_rows * b_tiles,
+                                              ctx->stream));
+            dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(ac, b, d2, ldc, tilemin,
+                                                                           b_tiles, nullptr, 0);
+            MCG_KERNEL_CHECK(ctx);
+        }
         mcg_timer_end(ctx, T_DIST);
-        MCG_KERNEL_CHECK(ctx);
         long long blocks = (ac.n + warps * kProbRows - 1) / (warps * kProbRows);
         const long long cap = 4LL * ctx->sm_count * 4;
         if (blocks > cap) blocks = cap;
@@ -1973,22 +2027,44 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
             MCG_CUDA(ctx, cudaMemsetAsync(cl.total, 0, 16, ctx->stream));
             long long bb = (ac.n + 7) / 8;
             if (bb > 8LL * ctx->sm_count) bb = 8LL * ctx->sm_count;
-            bound_kernel<<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
-                ac, b, S, d2, ldc, ctx->scratch[1].as<double>(), ldc, tilemin, cl, d_status);
+            if (use_tc)
+                bound_kernel<float><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
+                    ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl, d_status);
+            else
+                bound_kernel<double><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
+                    ac, b, S, d2, ldc, nullptr, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
+                    d_status);
             MCG_KERNEL_CHECK(ctx);
             const unsigned sb = static_cast<unsigned>(8 * ctx->sm_count);
             if (guard) {
-                cand_score_kernel<true><<<sb, 256, 0, ctx->stream>>>(ac, b, S, d2, ldc, cl, d_status);
+                if (use_tc)
+                    cand_score_kernel<true, true><<<sb, 256, 0, ctx->stream>>>(ac, b, S, nullptr, 0, cl,
+                                                                              d_status);
+                else
+                    cand_score_kernel<true, false><<<sb, 256, 0, ctx->stream>>>(ac, b, S, d2, ldc, cl,
+                                                                               d_status);
                 MCG_KERNEL_CHECK(ctx);
                 cand_argmin_kernel<true><<<blocks_for(ac.n, 256), 256, 0, ctx->stream>>>(
                     ac, cl, shifted, redo);
             } else {
-                cand_score_kernel<false><<<sb, 256, 0, ctx->stream>>>(ac, b, S, d2, ldc, cl, d_status);
+                if (use_tc)
+                    cand_score_kernel<false, true><<<sb, 256, 0, ctx->stream>>>(ac, b, S, nullptr, 0,
+                                                                               cl, d_status);
+                else
+                    cand_score_kernel<false, false><<<sb, 256, 0, ctx->stream>>>(ac, b, S, d2, ldc, cl,
+                                                                                d_status);
                 MCG_KERNEL_CHECK(ctx);
                 cand_argmin_kernel<false><<<blocks_for(ac.n, 256), 256, 0, ctx->stream>>>(
                     ac, cl, shifted, redo);
             }
             MCG_KERNEL_CHECK(ctx);
+            if (use_tc) {
+                // the candidate list overflowed (a device-side fact): the exact matrix after
+                // all, for prob_kernel below; one early-exit CTA wave otherwise
+                dist2_kernel<0><<<grid, kPairThreads, kDistSmem, ctx->stream>>>(
+                    ac, b, d2, ldc, nullptr, b_tiles, cl.total, cl.cap);
+                MCG_KERNEL_CHECK(ctx);
+            }
         }
         for (long long g0 = 0; g0 < b.n; g0 += group) {
             const int ncols = static_cast<int>(b.n - g0 < group ? b.n - g0 : group);
