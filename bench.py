@@ -283,6 +283,109 @@ def cpu_baseline(blob, offsets, coverage, cen_prof, cen_cov, budget_s, gpu_arg, 
     return base, parity
 
 
+def _reference_package():
+    for cand in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "metacoag_utils")):
+            return cand
+    return None
+
+
+def python_reference_worker(path):
+    """Child process of python_reference_baseline: a fresh interpreter (the reference forks a
+    multiprocessing.Pool; the parent holds CUDA contexts, NCCL threads and pinned memory)."""
+    import concurrent.futures
+    import importlib
+    import tempfile
+    pkg = _reference_package()
+    sys.path.append(os.path.join(ROOT, "tests", "cli_shims"))    # Bio stand-in (site-packages first)
+    sys.path.insert(0, pkg)
+    fu = importlib.import_module("metacoag_utils.feature_utils")
+    lpu = importlib.import_module("metacoag_utils.label_prop_utils")
+    data = np.load(path)
+    blob, offsets, coverage = data["blob"], data["offsets"], data["coverage"]
+    cen_prof, cen_cov, n_score = data["cen_prof"], data["cen_cov"], int(data["n_score"])
+    cores = os.cpu_count() or 1
+    seqs = [blob[offsets[i]:offsets[i + 1]].tobytes().decode("latin-1")
+            for i in range(offsets.shape[0] - 1)]
+    lengths = {k: len(q) for k, q in enumerate(seqs)}
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        profiles = fu.get_tetramer_profiles(tmp + "/", seqs, "contigs.fa", lengths, 0, cores)
+        scan_s = time.perf_counter() - t0
+    covs = {k: [max(float(v), 1e-4) for v in coverage[k]] for k in range(n_score)}
+    bin_prof = {b: cen_prof[b] for b in range(cen_prof.shape[0])}
+    bin_cov = {b: cen_cov[b] for b in range(cen_cov.shape[0])}
+    out = [None] * n_score
+
+    def work(k):
+        out[k] = lpu.assign_long(k, covs, profiles, bin_prof, bin_cov)
+    t0 = time.perf_counter()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(work, range(n_score)))
+    score_s = time.perf_counter() - t0
+    emit({"scan_s": scan_s, "score_s": score_s, "cores": cores, "pkg": pkg,
+          "arg": [-1 if r is None else int(r[1]) for r in out],
+          "w": [repr(sys.float_info.max if r is None else float(r[2])) for r in out]})
+
+
+def python_reference_baseline(blob, offsets, coverage, cen_prof, cen_cov, gpu_arg, gpu_w,
+                              n_scan=1500, n_score=160, seed=0):
+    """The reference's OWN Python code on this box's host cores, on seeded subsamples:
+    feature_utils.get_tetramer_profiles with ``nthreads = cpu_count`` (its multiprocessing.Pool,
+    feature_utils.py:73-119) and label_prop_utils.assign_long through the ThreadPoolExecutor of
+    metacoag:959-999, as shipped.  The unmodified modules come from /root/reference (build
+    container) or from baseline/_ref (the reference pip-installed once, unmodified, next to the
+    repo: it travels to the GPU box); Bio is the stand-in of tests/cli_shims where BioPython is
+    missing.  Results of the subsample are compared with the GPU's.  None when no copy exists."""
+    import tempfile
+    pkg = _reference_package()
+    if pkg is None:
+        return None
+    n = offsets.shape[0] - 1
+    rng = np.random.default_rng([seed, 31])
+    ids = np.sort(rng.choice(n, min(n, n_scan), replace=False))
+    n_score = min(n_score, ids.shape[0])
+    lens = (offsets[ids + 1] - offsets[ids]).astype(np.int64)
+    sub_off = np.zeros(ids.shape[0] + 1, dtype=np.int64)
+    np.cumsum(lens, out=sub_off[1:])
+    sub_blob = np.concatenate([blob[offsets[i]:offsets[i + 1]] for i in ids])
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "sample.npz")
+        np.savez(path, blob=sub_blob, offsets=sub_off, coverage=coverage[ids[:n_score]],
+                 cen_prof=cen_prof, cen_cov=cen_cov, n_score=n_score)
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "CUDA_VISIBLE_DEVICES")}
+        env["CUDA_VISIBLE_DEVICES"] = ""
+        try:
+            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--python-ref-worker",
+                                   path], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                  text=True, timeout=600)
+            res = json.loads(proc.stdout.strip().splitlines()[-1])
+        except Exception as err:   # a broken copy is not a reason to lose the bench line
+            return {"unavailable": "%s: %s" % (type(err).__name__, err)}
+    scan_s, score_s, cores = res["scan_s"], res["score_s"], res["cores"]
+    ref_arg = np.array(res["arg"], dtype=np.int32)
+    ref_w = np.array([float(x) for x in res["w"]])
+    bases = int(sub_off[-1])
+    sub = ids[:n_score]
+    mean_len = float(np.mean(np.diff(offsets)))
+    per_contig = scan_s / max(1, bases) * mean_len + score_s / max(1, n_score)
+    return {"value": 1.0 / per_contig, "unit": "contigs/s", "kind": "reference",
+            "extrapolated": True, "cores": cores,
+            "source": "metacoag_utils from %s" % ("/root/reference" if pkg == "/root/reference"
+                                                  else "baseline/_ref (pip install of the reference)"),
+            "scan": {"contigs": int(ids.shape[0]), "mbp": bases / 1e6, "seconds": scan_s,
+                     "mbp_per_s": bases / 1e6 / scan_s,
+                     "how": "feature_utils.get_tetramer_profiles, multiprocessing.Pool(%d)" % cores},
+            "score": {"contigs": int(n_score), "bins": int(cen_prof.shape[0]),
+                      "samples": int(coverage.shape[1]), "seconds": score_s,
+                      "us_per_pair": score_s * 1e6 / max(1, n_score * cen_prof.shape[0]),
+                      "how": "label_prop_utils.assign_long via ThreadPoolExecutor(%d), as metacoag:959-999" % cores},
+            "sample": "seeded subsample; per-contig cost = scan seconds per base x mean contig "
+                      "length + scoring seconds per contig, linear extrapolation",
+            "parity_vs_gpu": compare(gpu_arg[sub], gpu_w[sub], ref_arg, ref_w)}
+
+
 def config_dict(world, peer):
     """`config` of the headline line; the reference arm prints the same dict (the driver
     compares them key by key)."""
@@ -801,6 +904,12 @@ def run_config(rt, name, cfg, pool, args, hbm_peak, hbm_src, fp64_peak):
         entry["cpu_baseline"] = base
         entry["parity"] = parity
         entry["e2e_vs_cpu_port"] = e2e["value"] / base["value"]
+        if not os.environ.get("MCG_BENCH_NO_PYTHON_REF"):
+            # ~3 s of the reference's Python per configuration (B x S decides the cost per contig)
+            n_score = int(max(16, min(160, 3.0 / (B * (8e-6 + 0.8e-6 * S)))))
+            entry["cpu_baseline_python"] = python_reference_baseline(
+                hs.blob, hs.offsets, hs.coverage, cen_prof, cen_cov, arg, w, n_scan=1500,
+                n_score=n_score, seed=seed)
         if cfg.get("label_prop"):
             log(name, "label-propagation round")
             entry["label_prop_round"] = label_prop_round(pool, hs, B, seed)
@@ -830,6 +939,9 @@ def main():
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+    if len(sys.argv) == 3 and sys.argv[1] == "--python-ref-worker":
+        python_reference_worker(sys.argv[2])
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -1212,6 +1324,9 @@ def main():
                                     e2e_arg, e2e_w)
         line["cpu_baseline"] = base
         line["parity"] = parity
+        if not os.environ.get("MCG_BENCH_NO_PYTHON_REF"):
+            line["cpu_baseline_python"] = python_reference_baseline(
+                hs_blob, hs_off, hs_cov, cen_prof, cen_cov, e2e_arg, e2e_w)
         line["e2e"]["weak_scaling_note"] = (
             "e2e at N GPUs is one process (rank 0) driving all N through mcg_pool_*; the host "
             "reads N x %.2f GB of ASCII per step, so it is bound by host DRAM, not by the GPUs; "
