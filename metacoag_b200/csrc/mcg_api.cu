@@ -1567,7 +1567,15 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
     if (n <= 0) return mcg_fail(ctx, MCG_ERR_ARG, "no contigs");
     MCG_MARK("enter");
     const bool waves = offsets && offsets[n] >= (64 << 20) && !getenv("MCG_NO_WAVES");
-    MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples, !waves));
+    // The coverage table either goes first, in one copy (round 1), or its rows travel with their
+    // wave on a side stream.  Measured on the B200 box (A/B in one process, scratch/e2e_ab.py):
+    // per wave wins when the table is at least as large as the 2-bit contigs (5 M contigs x 100
+    // samples: 4 GB next to 3.5 GB -- e2e 337 -> 282 ms, the scans no longer wait for it) and
+    // loses below that (1 M x 50: 27.7 -> 36 ms; 100 k x 10: 6.5 -> 8.3 ms), so that is the switch.
+    // MCG_COV_WAVES=0 / 1 forces one or the other.
+    bool cov_waves = waves && 8.0 * static_cast<double>(n) * n_samples >= 0.25 * static_cast<double>(offsets[n]);
+    if (const char *env = getenv("MCG_COV_WAVES")) cov_waves = waves && atoi(env) != 0;
+    MCG_TRY(load_coverage_locked(ctx, cov, n, n_samples, !cov_waves));
     MCG_TRY(set_centroids_locked(ctx, cen_prof, cen_cov, n_bins, n_samples));
     MCG_MARK("cov+centroids queued");
     if (waves) {
@@ -1578,6 +1586,7 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
         // call's readers of the coverage tables)
         MCG_CUDA(ctx, cudaEventRecord(ctx->copy_start, ctx->stream));
         MCG_CUDA(ctx, cudaStreamWaitEvent(ctx->cov_stream, ctx->copy_start, 0));
+        if (!cov_waves) MCG_TRY(cov_terms_locked(ctx));
         MCG_TRY(mcg_reserve(ctx, ctx->counts, sizeof(uint32_t) * MCG_NPROF * n));
         MCG_TRY(mcg_reserve(ctx, ctx->prof, sizeof(double) * MCG_NPROF * n));
         MCG_TRY(mcg_reserve(ctx, ctx->prof_norm, sizeof(double) * n));
@@ -1587,7 +1596,7 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
         ctx->n_prof = n;
         const bool was_profiling = ctx->profiling;
         const WaveFactory factory = [&](const std::vector<ContigMeta> &meta, int64_t n_seg) -> WaveFn {
-            return [ctx, &meta, n_seg, n, cov](int64_t c0, int64_t c1) -> int {
+            return [ctx, &meta, n_seg, n, cov, cov_waves](int64_t c0, int64_t c1) -> int {
                 if (c1 <= c0) return MCG_OK;
                 const bool prof = ctx->profiling;
                 ctx->profiling = false;   // one event pair per timer: the waves share T_H2D
@@ -1604,7 +1613,7 @@ extern "C" int mcg_featurise_score(mcg_ctx *ctx, const uint8_t *bases, const int
                 // coverage rows of the range: queued on the side stream now (they travel and are
                 // featurised under the kernels of the waves in front); the compute stream waits
                 // for them here, behind this range's scan
-                if (rc == MCG_OK) rc = wave_coverage(ctx, cov, c0, c1);
+                if (rc == MCG_OK && cov_waves) rc = wave_coverage(ctx, cov, c0, c1);
                 if (rc == MCG_OK) {
                     ScoreSide a = contig_side(ctx, nullptr, c1 - c0);
                     a.first = c0;

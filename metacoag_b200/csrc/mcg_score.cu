@@ -1428,20 +1428,31 @@ __device__ __forceinline__ void ld_v4(double (&v)[4], const double *p) {
 // of FMAs over k in ascending order (experiments/dmma_fma_chain.cu: 262 144 of 262 144 outputs
 // bit-equal on the B200), the norms are the DMMA norms of row_norms_kernel, and the epilogue is
 // dist2_kernel's fma(-2, u.v, |u|^2 + |v|^2) clamped at 0.
+// N x 4 slots of the chain: all 2 N loads (32 bytes each; rows are 32-byte aligned, 136 x 8 =
+// 34 x 32) are in flight before the first FMA needs one -- a lane walks its own two rows, and
+// with one load per FMA group the walk paid an L2 round trip per 32 bytes
+template <int N>
+__device__ __forceinline__ double fma_chain(const double *u, const double *v, double acc) {
+    double a[N][4], b[N][4];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        ld_v4(a[i], u + 4 * i);
+        ld_v4(b[i], v + 4 * i);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc = fma(a[i][q], b[i][q], acc);
+    return acc;
+}
+
 __device__ __forceinline__ double exact_d2(const ScoreSide &A, const ScoreSide &B, long long arow,
                                            long long brow) {
     const double *u = A.prof + arow * MCG_NPROF, *v = B.prof + brow * MCG_NPROF;
-    double acc = 0.0;
-#pragma unroll 2
-    for (int k = 0; k < MCG_NPROF; k += 4) {   // rows are 32-byte aligned (136 x 8 = 34 x 32)
-        double a[4], b[4];
-        ld_v4(a, u + k);
-        ld_v4(b, v + k);
-        acc = fma(a[0], b[0], acc);
-        acc = fma(a[1], b[1], acc);
-        acc = fma(a[2], b[2], acc);
-        acc = fma(a[3], b[3], acc);
-    }
+    double acc = fma_chain<9>(u, v, 0.0);          // k = 0 .. 35
+    acc = fma_chain<9>(u + 36, v + 36, acc);       //     36 .. 71
+    acc = fma_chain<8>(u + 72, v + 72, acc);       //     72 .. 103
+    acc = fma_chain<8>(u + 104, v + 104, acc);     //    104 .. 135
     const double d2 = fma(-2.0, acc, A.norm[arow] + B.norm[brow]);
     return d2 > 0.0 ? d2 : 0.0;
 }
