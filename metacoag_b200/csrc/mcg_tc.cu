@@ -255,22 +255,28 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int acc = j & 1;
             mbar_wait(acc_full + acc, (j >> 1) & 1);
             tc_fence_after();
-            float tmin[2] = {INFINITY, INFINITY};
+            // |x_v|^2 is padded with +inf up to ldf (tc_prep_kernel), so a column beyond the bins
+            // comes out as +inf without a test per element: it never is a minimum, and its
+            // store lands in the padding of d2a
+            float tmin0 = INFINITY, tmin1 = INFINITY;
 #pragma unroll 1
             for (int c = 0; c < kTcN / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * quarter) << 16) +
                               static_cast<uint32_t>(acc * kTcN + 32 * c), v);
-                const long long col0 = static_cast<long long>(j) * kTcN + 32 * c;
+                const int col0 = j * kTcN + 32 * c;
+                const float4 *nv4 = reinterpret_cast<const float4 *>(a.nv + col0);
                 float lo = INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const long long col = col0 + i;
-                    const float nvc = col < a.bins ? __ldg(a.nv + col) : 0.f;
-                    v[i] = fmaf(v[i], inv_s2, nu + nvc);
-                    if (col < a.bins) lo = fminf(lo, v[i]);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 n = __ldg(nv4 + (i >> 2));
+                    v[i] = fmaf(v[i], inv_s2, nu + n.x);
+                    v[i + 1] = fmaf(v[i + 1], inv_s2, nu + n.y);
+                    v[i + 2] = fmaf(v[i + 2], inv_s2, nu + n.z);
+                    v[i + 3] = fmaf(v[i + 3], inv_s2, nu + n.w);
+                    lo = fminf(fminf(lo, fminf(v[i], v[i + 1])), fminf(v[i + 2], v[i + 3]));
                 }
-                tmin[c >> 1] = fminf(tmin[c >> 1], lo);
+                if (c < 2) tmin0 = fminf(tmin0, lo); else tmin1 = fminf(tmin1, lo);
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -286,7 +292,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int h = 0; h < 2; ++h) {
                     const long long t64 = 2LL * j + h;
                     if (t64 < a.nbt64) {
-                        const double lb = fmax(static_cast<double>(tmin[h]) - static_cast<double>(mrow), 0.0);
+                        const double lb = fmax(static_cast<double>(h ? tmin1 : tmin0) - static_cast<double>(mrow), 0.0);
                         a.tilemin[row * a.nbt64 + t64] =
                             static_cast<unsigned long long>(__double_as_longlong(lb));
                     }
@@ -313,10 +319,13 @@ template <bool B_SIDE>
 __global__ void __launch_bounds__(256)
 tc_prep_kernel(const double *__restrict__ prof, const int64_t *__restrict__ index, long long first,
                long long rows, __half *__restrict__ out, float *__restrict__ norm2,
-               float *__restrict__ norm1) {
+               float *__restrict__ norm1, long long pad_to) {
     const long long r = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (r >= rows) return;
+    if (r >= rows) {
+        if (r < pad_to && lane == 0) norm2[r] = INFINITY;   // see the epilogue of tc_dist_kernel
+        return;
+    }
     const long long src = index ? index[first + r] : (first + r);
     const double *p = prof + src * MCG_NPROF;
     __half *o = out + r * kTcK;
@@ -429,11 +438,13 @@ long long mcg_tc_ldf(long long bins) { return (bins + kTcN - 1) / kTcN * kTcN; }
 int mcg_k_tc_prep_bins(mcg_ctx *ctx, const ScoreSide &b) {
     MCG_TRY(ensure_tc(ctx));
     MCG_TRY(mcg_reserve(ctx, ctx->tc_b, sizeof(__half) * kTcK * b.n));
-    MCG_TRY(mcg_reserve(ctx, ctx->tc_baux, sizeof(float) * (2 * b.n + 4)));
+    // [|x_v|^2, padded with +inf to ldf] [|x_v| bins] [max |x_v|]
+    const long long ldf = mcg_tc_ldf(b.n);
+    MCG_TRY(mcg_reserve(ctx, ctx->tc_baux, sizeof(float) * (ldf + b.n + 4)));
     float *nv = ctx->tc_baux.as<float>();
-    float *n1 = nv + b.n;
-    tc_prep_kernel<true><<<static_cast<unsigned>((b.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        b.prof, b.index, b.first, b.n, ctx->tc_b.as<__half>(), nv, n1);
+    float *n1 = nv + ldf;
+    tc_prep_kernel<true><<<static_cast<unsigned>((ldf * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        b.prof, b.index, b.first, b.n, ctx->tc_b.as<__half>(), nv, n1, ldf);
     MCG_KERNEL_CHECK(ctx);
     tc_bmax_kernel<<<1, 256, 0, ctx->stream>>>(n1, b.n, n1 + b.n);
     MCG_KERNEL_CHECK(ctx);
@@ -453,11 +464,11 @@ int mcg_k_tc_dist(mcg_ctx *ctx, const ScoreSide &a, long long bins, float *d_d2a
     float *nu = ctx->tc_aaux.as<float>();
     float *n1 = nu + a.n;
     tc_prep_kernel<false><<<static_cast<unsigned>((a.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        a.prof, a.index, a.first, a.n, ctx->tc_a.as<__half>(), nu, n1);
+        a.prof, a.index, a.first, a.n, ctx->tc_a.as<__half>(), nu, n1, 0);
     MCG_KERNEL_CHECK(ctx);
     const float *bn = ctx->tc_baux.as<float>();
     tc_margin_kernel<<<static_cast<unsigned>((a.n + 255) / 256), 256, 0, ctx->stream>>>(
-        n1, bn + 2 * bins, a.n, d_mrow);
+        n1, bn + mcg_tc_ldf(bins) + bins, a.n, d_mrow);
     MCG_KERNEL_CHECK(ctx);
     CUtensorMap map_a, map_b;
     MCG_TRY(make_map(ctx, &map_a, ctx->tc_a.as<__half>(), a.n));
