@@ -18,17 +18,20 @@
 // ruled out only when even d2a - margin is beyond the threshold, and every listed pair gets its
 // exact float64 d^2 again (mcg_score.cu, exact_d2), so argmin and weights keep their bits.
 //
-// Kernel shape (one CTA = 128 contigs against all bins, 6 warps, warp-specialised):
-//   warp 0   TMA producer: the CTA's A' tile (7 k-blocks of 128 rows x 128 bytes, SWIZZLE_128B)
-//            once, resident; the B' tiles of every 128-bin block through a 4-stage ring
+// Kernel shape (persistent: one CTA per SM walks 128-contig row tiles; 6 warps, warp-specialised):
+//   warp 0   TMA producer: the row tile's A' (7 k-blocks of 128 rows x 128 bytes, SWIZZLE_128B),
+//            resident while the tile's bin blocks run, one full / empty mbarrier pair per
+//            k-block so that the NEXT row tile streams in under the MMAs of the last bin block;
+//            the B' tiles of every 128-bin block through a 4-stage ring
 //            (cp.async.bulk.tensor.2d + mbarrier complete_tx);
 //   warp 1   MMA issuer: one elected lane issues 4 tcgen05.mma (M 128, N 128, K 16) per
-//            k-block, tcgen05.commit frees the ring slot / publishes the accumulator; two
-//            accumulator stages (2 x 128 TMEM columns) so that the epilogue of bin block j
-//            runs under the MMAs of block j + 1;
+//            k-block, tcgen05.commit frees the ring slot (and, in the last bin block, the A'
+//            k-block) / publishes the accumulator; two accumulator stages (2 x 128 TMEM
+//            columns) so that the epilogue of one block runs under the MMAs of the next, across
+//            row tiles as well;
 //   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> d2a in fp32 ->
 //            128-byte stores of the thread's row, plus the smallest lower bound per 64-bin tile.
-// Bound: HBM (896 B of A' in and 4 B per pair out per contig; the MMAs are ~1 us per CTA).
+// Bound: HBM (896 B of A' in and 4 B per pair out per contig; the MMAs are ~1 us per row tile).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -45,7 +48,7 @@ constexpr int kTcStages = 4;                   // B' ring
 constexpr int kTcTileBytes = kTcM * kTcKB * 2; // 16 KB per k-block of either operand
 constexpr int kTcThreads = 192;
 constexpr double kTcScale = 4096.0;            // x * 2^12 = hi + lo
-constexpr size_t kTcSmem = 1024 + static_cast<size_t>(kTcKBlocks + kTcStages) * kTcTileBytes + 256;
+constexpr size_t kTcSmem = 1024 + static_cast<size_t>(kTcKBlocks + kTcStages) * kTcTileBytes + 512;
 
 // ---- PTX wrappers (sm_100a) -------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -173,21 +176,22 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t *sm_a = base;                                   // [7][16 KB] resident
     uint8_t *sm_b = base + kTcKBlocks * kTcTileBytes;       // [4][16 KB] ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm_b + kTcStages * kTcTileBytes);
-    uint64_t *a_full = bars;                                // [1]
-    uint64_t *b_full = bars + 1;                            // [stages]
+    uint64_t *a_full = bars;                                // [k-blocks]
+    uint64_t *a_empty = a_full + kTcKBlocks;                // [k-blocks]
+    uint64_t *b_full = a_empty + kTcKBlocks;                // [stages]
     uint64_t *b_empty = b_full + kTcStages;                 // [stages]
     uint64_t *acc_full = b_empty + kTcStages;               // [2]
     uint64_t *acc_empty = acc_full + 2;                     // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long m0 = static_cast<long long>(blockIdx.x) * kTcM;
     const int n_tiles = static_cast<int>((a.bins + kTcN - 1) / kTcN);
+    const long long m_tiles = (a.rows + kTcM - 1) / kTcM;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        mbar_init(a_full, 1);
+        for (int s = 0; s < kTcKBlocks; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
         for (int s = 0; s < kTcStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
         fence_barrier_init();
@@ -201,32 +205,40 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(a_full, kTcKBlocks * kTcTileBytes);
-            for (int kb = 0; kb < kTcKBlocks; ++kb)
-                tma_load_2d(&map_a, a_full, sm_a + kb * kTcTileBytes, kb * kTcKB, static_cast<int>(m0));
             int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_tiles; ++j)
+            uint32_t phase = 0, it = 0;
+            for (long long mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+                // k-block kb of A' is free again when the MMAs of the previous row tile's last
+                // bin tile have read it: the next row tile streams in under those MMAs
                 for (int kb = 0; kb < kTcKBlocks; ++kb) {
-                    mbar_wait(b_empty + stage, phase ^ 1);
-                    mbar_expect_tx(b_full + stage, kTcTileBytes);
-                    tma_load_2d(&map_b, b_full + stage, sm_b + stage * kTcTileBytes, kb * kTcKB,
-                                j * kTcN);
-                    if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                    mbar_wait(a_empty + kb, (it & 1) ^ 1);
+                    mbar_expect_tx(a_full + kb, kTcTileBytes);
+                    tma_load_2d(&map_a, a_full + kb, sm_a + kb * kTcTileBytes, kb * kTcKB,
+                                static_cast<int>(mt * kTcM));
                 }
+                for (int j = 0; j < n_tiles; ++j)
+                    for (int kb = 0; kb < kTcKBlocks; ++kb) {
+                        mbar_wait(b_empty + stage, phase ^ 1);
+                        mbar_expect_tx(b_full + stage, kTcTileBytes);
+                        tma_load_2d(&map_b, b_full + stage, sm_b + stage * kTcTileBytes, kb * kTcKB,
+                                    j * kTcN);
+                        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+                    }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            mbar_wait(a_full, 0);
             int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_tiles; ++j) {
-                const int acc = j & 1;
-                mbar_wait(acc_empty + acc, ((j >> 1) & 1) ^ 1);   // the epilogue has drained it
+            uint32_t phase = 0, it = 0, tile = 0;
+            for (long long mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it)
+            for (int j = 0; j < n_tiles; ++j, ++tile) {
+                const uint32_t acc = tile & 1;
+                mbar_wait(acc_empty + acc, ((tile >> 1) & 1) ^ 1);   // the epilogue has drained it
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTcN);
+                const uint32_t tmem_d = tmem_base + acc * kTcN;
                 for (int kb = 0; kb < kTcKBlocks; ++kb) {
+                    if (j == 0) mbar_wait(a_full + kb, it & 1);
                     mbar_wait(b_full + stage, phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sm_a + kb * kTcTileBytes);
@@ -237,6 +249,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                  umma_desc_sw128(b_addr + 32 * k), kTcIdesc,
                                  (kb | k) != 0 ? 1u : 0u);
                     umma_commit(b_empty + stage);            // slot free when these MMAs are done
+                    if (j == n_tiles - 1) umma_commit(a_empty + kb);   // A' k-block free as well
                     if (++stage == kTcStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(acc_full + acc);                 // accumulator ready for the epilogue
@@ -245,15 +258,17 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
         const int quarter = warp & 3;
-        const long long row = m0 + 32 * quarter + lane;
+        const float inv_s2 = static_cast<float>(-2.0 / (kTcScale * kTcScale));
+        uint32_t tile = 0;
+        for (long long mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        const long long row = mt * kTcM + 32 * quarter + lane;
         const bool row_ok = row < a.rows;
         const float nu = row_ok ? a.nu[row] : 0.f;
         const float mrow = row_ok ? a.mrow[row] : 0.f;
-        const float inv_s2 = static_cast<float>(-2.0 / (kTcScale * kTcScale));
         float *out_row = a.d2a + row * a.ldf;
-        for (int j = 0; j < n_tiles; ++j) {
-            const int acc = j & 1;
-            mbar_wait(acc_full + acc, (j >> 1) & 1);
+        for (int j = 0; j < n_tiles; ++j, ++tile) {
+            const uint32_t acc = tile & 1;
+            mbar_wait(acc_full + acc, (tile >> 1) & 1);
             tc_fence_after();
             // |x_v|^2 is padded with +inf up to ldf (tc_prep_kernel), so a column beyond the bins
             // comes out as +inf without a test per element: it never is a minimum, and its
@@ -263,7 +278,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int c = 0; c < kTcN / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * quarter) << 16) +
-                              static_cast<uint32_t>(acc * kTcN + 32 * c), v);
+                              (acc * kTcN + 32u * c), v);
                 const int col0 = j * kTcN + 32 * c;
                 const float4 *nv4 = reinterpret_cast<const float4 *>(a.nv + col0);
                 float lo = INFINITY;
@@ -298,6 +313,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+        }
         }
     }
     tc_fence_before();
@@ -483,7 +499,9 @@ int mcg_k_tc_dist(mcg_ctx *ctx, const ScoreSide &a, long long bins, float *d_d2a
     args.nbt64 = nbt64;
     args.rows = a.n;
     args.bins = bins;
-    tc_dist_kernel<<<static_cast<unsigned>(tiles), kTcThreads, kTcSmem, ctx->stream>>>(map_a, map_b,
+    // persistent: one CTA per SM walks row tiles blockIdx.x, blockIdx.x + grid, ...
+    const long long grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    tc_dist_kernel<<<static_cast<unsigned>(grid), kTcThreads, kTcSmem, ctx->stream>>>(map_a, map_b,
                                                                                        args);
     MCG_KERNEL_CHECK(ctx);
     return MCG_OK;
