@@ -1211,18 +1211,129 @@ __global__ void bin_head_kernel(ScoreSide B, int S, int nq, long long ldh,
     head[(2 * q + 1) * ldh + j] = B.logc[brow * S + q];
 }
 
+__device__ __forceinline__ void ld_v4(double (&v)[4], const double *p) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+// What bound_kernel needs to know about a contig before it looks at bins: the weight W of its
+// nearest centroid, the distance threshold that follows from it, and the coverage ceilings.
+struct BoundPre {
+    double w, thr2, u_tail, cov_upper;
+    int jm, pad;
+};
+
+__device__ __forceinline__ double prune_threshold(double wv, double cov_upper) {
+    // parabola(d) > W ln 10 + U  <=>  d > (-qb + sqrt(qb^2 + 4 qa target)) / (2 qa)
+    const double target = wv * (1.0 + 1e-9) * c_gauss.ln10 + cov_upper - c_math.prune_c;
+    double disc = fma(c_math.prune_4a, target, c_math.prune_b * c_math.prune_b);
+    if (!(disc > 0.0)) disc = 0.0;
+    double d = (sqrt(disc) - c_math.prune_b) * c_math.prune_inv_2a;
+    d = d > 0.0 ? d * (1.0 + 1e-9) : 0.0;
+    return d * d * (1.0 + 1e-15);
+}
+
+// One LANE per contig (tensor-core distances): nearest centroid from the tile minima and the 64
+// d2a of that tile, U and its tail, W = the weight of the nearest centroid at the upper end of
+// its distance interval, the threshold.  In bound_kernel this is ~700 warp instructions per
+// contig that are the same in all 32 lanes (ncu source page, r02h); here it is ~20.  The sums
+// run in sample order instead of a shuffle tree: W is a bound used with a 1e-9 margin, not a
+// result.
+__global__ void __launch_bounds__(128)
+bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, long long ldc,
+                 const float *__restrict__ mrow, const unsigned long long *__restrict__ tilemin,
+                 BoundPre *__restrict__ pre, int32_t *__restrict__ status) {
+    __shared__ double ET[16];
+    __shared__ double LT[128];
+    const int tid = threadIdx.x;
+    if (tid < 16) ET[tid] = g_exp_table[tid];
+    if (tid < 128) LT[tid] = g_log_table[tid];
+    __syncthreads();
+    const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + tid;
+    const bool live = r < A.n;
+    const long long rr = live ? r : 0;
+    const int nb = static_cast<int>(B.n);
+    const int nbt = (nb + 63) >> 6;
+    const int nq = S < kHeadSamples ? S : kHeadSamples;
+    const double sl = static_cast<double>(S) * c_math.log_floor;
+    // nearest centroid (first index on ties): the tile with the smallest minimum, then its bins
+    unsigned long long bk = ~0ull;
+    int bt = 0;
+    for (int t = 0; t < nbt; ++t) {
+        const unsigned long long key = tilemin[rr * nbt + t];
+        if (key < bk) { bk = key; bt = t; }
+    }
+    const float *row = d2 + rr * ldc + 64 * bt;
+    float dmf = INFINITY;
+    int jm = 64 * bt;
+#pragma unroll 4
+    for (int i = 0; i < 64; i += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(row + i);   // padding reads +inf
+        if (v.x < dmf) { dmf = v.x; jm = 64 * bt + i; }
+        if (v.y < dmf) { dmf = v.y; jm = 64 * bt + i + 1; }
+        if (v.z < dmf) { dmf = v.z; jm = 64 * bt + i + 2; }
+        if (v.w < dmf) { dmf = v.w; jm = 64 * bt + i + 3; }
+    }
+    if (jm >= nb) { jm = 0; dmf = INFINITY; }
+    const double mg = static_cast<double>(mrow[rr]);
+    const double dd = static_cast<double>(dmf) + mg;
+    const bool ok = dd < 0.03;   // d < 0.17: prob_comp normal with room to spare
+    const long long arow = A.index ? A.index[A.first + rr] : (A.first + rr);
+    const long long brow = B.index ? B.index[B.first + jm] : (B.first + jm);
+    const double *ac_p = A.cov + arow * S, *al_p = A.logc + arow * S, *ag_p = A.lgam + arow * S;
+    const double *bc_p = B.cov + brow * S, *bl_p = B.logc + brow * S, *bg_p = B.lgam + brow * S;
+    double u = 0.0, u_tail = 0.0, s1 = 0.0, s2 = 0.0;
+    auto sample = [&](int q, double ac, double al, double ag, double bc, double bl, double bg) {
+        const double am = -(ag + c_math.log_floor);
+        double e = fma(ac, al, am) - ac;   // the most this sample can add
+        e = e > 0.0 ? e : 0.0;
+        u += e;
+        if (q >= nq) u_tail += e;
+        add_poisson_excess(s1, ac, am, bc, bl);
+        add_poisson_excess(s2, bc, -(bg + c_math.log_floor), ac, al);
+    };
+    if ((S & 3) == 0) {
+#pragma unroll 1
+        for (int h = 0; h < S; h += 4) {
+            double ac[4], al[4], ag[4], bc[4], bl[4], bg[4];
+            ld_v4(ac, ac_p + h); ld_v4(al, al_p + h); ld_v4(ag, ag_p + h);
+            ld_v4(bc, bc_p + h); ld_v4(bl, bl_p + h); ld_v4(bg, bg_p + h);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sample(h + k, ac[k], al[k], ag[k], bc[k], bl[k], bg[k]);
+        }
+    } else {
+#pragma unroll 2
+        for (int q = 0; q < S; ++q) sample(q, ac_p[q], al_p[q], ag_p[q], bc_p[q], bl_p[q], bg_p[q]);
+    }
+    double cov_upper = fma(u, 1.0 + 1e-9, sl);   // U, rounded up
+    if (cov_upper > 0.0) cov_upper = 0.0;
+    const double lpc = log_comp_prob_warp(ok ? dd : 0.01, ET, LT, status);
+    const double w = ok ? -(lpc + sl + (s1 < s2 ? s1 : s2)) * c_math.inv_ln10 : INFINITY;
+    if (live) {
+        BoundPre out;
+        out.w = w;
+        out.thr2 = (w < kPruneMaxWeight) ? prune_threshold(w, cov_upper) : INFINITY;
+        out.u_tail = u_tail;
+        out.cov_upper = cov_upper;
+        out.jm = jm;
+        out.pad = 0;
+        pre[r] = out;
+    }
+}
+
 // D2T = double: d2 is dist2_kernel's exact matrix (mrow = nullptr).  D2T = float: d2 is the
 // tensor-core estimate d2a of mcg_tc.cu and mrow[r] the margin within which every d2a of row r
 // lies around the true d^2.  Every use of a distance below is one-sided, so it takes the side of
 // the interval that keeps the bound valid: ruling a bin OUT compares the LOWER end
 // (d2a - margin), and the weight W of a probed bin -- which only has to be AT LEAST the weight
 // of some bin -- is evaluated at the UPPER end (the weight grows with the distance).
-template <typename D2T>
+// PRE: W, the threshold and the coverage ceilings of every contig come from bound_pre_kernel.
+template <typename D2T, bool PRE>
 __global__ void __launch_bounds__(256)
 bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long long ldc,
              const float *__restrict__ mrow, const double *__restrict__ head, long long ldh,
              const unsigned long long *__restrict__ tilemin, CandList cl,
-             int32_t *__restrict__ status) {
+             int32_t *__restrict__ status, const BoundPre *__restrict__ pre) {
     __shared__ double ET[16];
     __shared__ double LT[128];
     __shared__ double HA[8][2 * kHeadSamples];   // per warp: (c, m) of the contig's first samples
@@ -1245,6 +1356,19 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
         const unsigned long long tile_key = lane < nbt ? tilemin[r * nbt + lane] : ~0ull;
         const double tile_d2 = __longlong_as_double(static_cast<long long>(
             tile_key <= 0x7ff0000000000000ull ? tile_key : 0x7ff0000000000000ull));
+        const long long arow = A.index ? A.index[A.first + r] : (A.first + r);
+        double dm = INFINITY, u_tail = 0.0, cov_upper = 0.0, w_pre = INFINITY, thr_pre = INFINITY;
+        int jm = 0;
+        __syncwarp();
+        if (PRE) {
+            const BoundPre bp = pre[r];
+            w_pre = bp.w; thr_pre = bp.thr2; u_tail = bp.u_tail; cov_upper = bp.cov_upper; jm = bp.jm;
+            if (lane < nq) {
+                HA[wid][2 * lane] = A.cov[arow * S + lane];
+                HA[wid][2 * lane + 1] = -(A.lgam[arow * S + lane] + c_math.log_floor);
+            }
+            __syncwarp();
+        } else {
         // nearest centroid (first index on ties): the tile with the smallest minimum, then its bins
         unsigned long long bk = tile_key;
         int bt_near = lane;
@@ -1254,8 +1378,6 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
             const int ot = __shfl_xor_sync(0xffffffffu, bt_near, m);
             if (ok < bk || (ok == bk && ot < bt_near)) { bk = ok; bt_near = ot; }
         }
-        double dm = INFINITY;
-        int jm = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int j = 64 * bt_near + 32 * h + lane;
@@ -1272,9 +1394,7 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
         }
         // the contig's side: U (and its tail beyond the head samples), head terms for the
         // coverage-aware test
-        const long long arow = A.index ? A.index[A.first + r] : (A.first + r);
-        double u = 0.0, u_tail = 0.0;   // lanes over samples
-        __syncwarp();
+        double u = 0.0;   // lanes over samples
         for (int q = lane; q < S; q += 32) {
             const double ac = A.cov[arow * S + q], al = A.logc[arow * S + q];
             const double am = -(A.lgam[arow * S + q] + c_math.log_floor);
@@ -1290,8 +1410,9 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
             u_tail += __shfl_xor_sync(0xffffffffu, u_tail, m);
         }
         __syncwarp();
-        double cov_upper = fma(u, 1.0 + 1e-9, sl);   // U, rounded up
+        cov_upper = fma(u, 1.0 + 1e-9, sl);   // U, rounded up
         if (cov_upper > 0.0) cov_upper = 0.0;
+        }
         // weight of one bin, by the whole warp (NaN: prob_comp is 0 or not a plain number)
         auto probe = [&](int j, double dd) -> double {
             if (!(dd < 0.03)) return INFINITY;   // d < 0.17: prob_comp normal with room to spare
@@ -1313,18 +1434,10 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
             const double lpc = log_comp_prob_warp(dd, ET, LT, status);
             return -(lpc + sl + (s1 < s2 ? s1 : s2)) * c_math.inv_ln10;
         };
-        double w = probe(jm, dm + mg);
-        // parabola(d) > W ln 10 + U  <=>  d > (-qb + sqrt(qb^2 + 4 qa target)) / (2 qa)
-        auto threshold = [&](double wv) -> double {
-            const double target = wv * (1.0 + 1e-9) * c_gauss.ln10 + cov_upper - c_math.prune_c;
-            double disc = fma(c_math.prune_4a, target, c_math.prune_b * c_math.prune_b);
-            if (!(disc > 0.0)) disc = 0.0;
-            double d = (sqrt(disc) - c_math.prune_b) * c_math.prune_inv_2a;
-            d = d > 0.0 ? d * (1.0 + 1e-9) : 0.0;
-            return d * d * (1.0 + 1e-15);
-        };
+        double w = PRE ? w_pre : probe(jm, dm + mg);
+        auto threshold = [&](double wv) -> double { return prune_threshold(wv, cov_upper); };
         const int n_slabs = static_cast<int>((B.n + 31) >> 5);
-        double thr2 = (w < kPruneMaxWeight) ? threshold(w) : INFINITY;
+        double thr2 = PRE ? thr_pre : ((w < kPruneMaxWeight) ? threshold(w) : INFINITY);
         if (!(thr2 < 0.045 * 0.045) && nq > 0) {
             // The nearest centroid gave no bound, or a loose one (short contigs sit as close to
             // a neighbour's centroid as to their own).  Second probe: the bin with the smallest
@@ -1339,9 +1452,12 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
                     const double dd = fmax(static_cast<double>(row[j]) - mg, 0.0);
                     double e1 = 0.0;
                     const double *hp = head + j;
-                    for (int q = 0; q < nq; ++q)
-                        add_poisson_excess(e1, HA[wid][2 * q], HA[wid][2 * q + 1],
-                                           hp[(2 * q) * ldh], hp[(2 * q + 1) * ldh]);
+                    // (four samples' loads in flight: this loop waits for L2, ncu r02o)
+#pragma unroll 4
+                    for (int q = 0; q < nq; ++q) {
+                        const double bc = hp[(2 * q) * ldh], bl = hp[(2 * q + 1) * ldh];
+                        add_poisson_excess(e1, HA[wid][2 * q], HA[wid][2 * q + 1], bc, bl);
+                    }
                     const double v = fma(c_math.prune_4a * 0.25, dd, -e1);
                     if (v < lb) { lb = v; jb = j; }
                 }
@@ -1414,11 +1530,6 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
             }
         }
     }
-}
-
-__device__ __forceinline__ void ld_v4(double (&v)[4], const double *p) {
-    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
-                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
 // One thread per listed pair: the weight prob_kernel computes for it, operation for operation
@@ -1931,6 +2042,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         MCG_CUDA(ctx, cudaFuncSetAttribute(prob_kernel<true, 16>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            200 * 1024));
+
         if (ctx->device < 64) attr[ctx->device] = true;
     }
     // rows per chunk: <= 512 MiB of scratch, whole tiles
@@ -1990,12 +2102,19 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
     const bool use_tc = use_cand && ctx->tc;
     const long long ldf = mcg_tc_ldf(b.n);
     float *d2a = nullptr, *mrow = nullptr;
+    BoundPre *pre = nullptr;
+    // the lane-per-contig pre-pass pays where the per-contig scalar work dominates bound_kernel
+    // (S <= 30; measured: cfg2 probability phase 0.280 -> 0.248 ms, cfg3 / cfg5 shards +2 %)
+    const bool bound_single = guard || getenv("MCG_BOUND_SINGLE") != nullptr;
     if (use_tc) {
         const long long rows_pad = (need_rows + 127) / 128 * 128;
         MCG_TRY(mcg_reserve(ctx, ctx->tc_d2a, sizeof(float) * rows_pad * ldf));
-        MCG_TRY(mcg_reserve(ctx, ctx->tc_mrow, sizeof(float) * need_rows));
+        // [margin need_rows floats, padded to 16 bytes] [BoundPre need_rows]
+        const size_t mrow_bytes = (sizeof(float) * need_rows + 15) / 16 * 16;
+        MCG_TRY(mcg_reserve(ctx, ctx->tc_mrow, mrow_bytes + sizeof(BoundPre) * need_rows));
         d2a = ctx->tc_d2a.as<float>();
         mrow = ctx->tc_mrow.as<float>();
+        pre = reinterpret_cast<BoundPre *>(ctx->tc_mrow.as<char>() + mrow_bytes);
         MCG_TRY(mcg_k_tc_prep_bins(ctx, b));
     }
     const CandGate gate = {cl.total, cl.cap};
@@ -2038,13 +2157,21 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
             MCG_CUDA(ctx, cudaMemsetAsync(cl.total, 0, 16, ctx->stream));
             long long bb = (ac.n + 7) / 8;
             if (bb > 8LL * ctx->sm_count) bb = 8LL * ctx->sm_count;
-            if (use_tc)
-                bound_kernel<float><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
-                    ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl, d_status);
+            if (use_tc && !bound_single) {
+                bound_pre_kernel<<<blocks_for(ac.n, 128), 128, 0, ctx->stream>>>(
+                    ac, b, S, d2a, ldf, mrow, tilemin, pre, d_status);
+                MCG_KERNEL_CHECK(ctx);
+                bound_kernel<float, true><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
+                    ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
+                    d_status, pre);
+            } else if (use_tc)
+                bound_kernel<float, false><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
+                    ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
+                    d_status, nullptr);
             else
-                bound_kernel<double><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
+                bound_kernel<double, false><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
                     ac, b, S, d2, ldc, nullptr, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
-                    d_status);
+                    d_status, nullptr);
             MCG_KERNEL_CHECK(ctx);
             const unsigned sb = static_cast<unsigned>(8 * ctx->sm_count);
             if (guard) {
