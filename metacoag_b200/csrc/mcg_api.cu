@@ -1267,87 +1267,147 @@ extern "C" int mcg_labels_set(mcg_ctx *ctx, const int64_t *ids, const int32_t *b
     return sync(ctx);   // ids / bins are the caller's again
 }
 
-extern "C" int mcg_bfs_resident(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts,
-                                int depth_limit, int64_t *hit_start, int32_t *hit_count,
-                                int32_t *hits, int64_t hit_cap, int64_t *total) {
-    MCG_ENTER(ctx);
+namespace {
+struct WalkHead { long long total; int n_redo, n_failed; };
+
+size_t walk_head_bytes(int64_t n_starts) {
+    const int64_t n8 = (n_starts + 1) / 2 * 2;
+    return 16 + 8 * static_cast<size_t>(n_starts) + 8 * static_cast<size_t>(n8);
+}
+
+// The walks that did not fit their shared-memory table again, over tables in global memory.
+int walk_redo(mcg_ctx *ctx, int64_t n_starts, int depth_limit, int64_t hit_cap, WalkHead *head) {
+    char *blk = ctx->g_block.as<char>();
+    for (int64_t stride = 4096;; stride *= 4) {
+        const size_t bytes = sizeof(int32_t) * static_cast<size_t>(stride) * head->n_redo;
+        if (bytes > (size_t(8) << 30))
+            return mcg_fail(ctx, MCG_ERR_NOMEM, "BFS work buffer would exceed 8 GiB");
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], bytes));
+        MCG_TRY(mcg_k_walks_redo(ctx, ctx->g_indptr.as<int64_t>(), ctx->g_indices.as<int32_t>(),
+                                 ctx->g_labels.as<int32_t>(), ctx->g_starts.as<int64_t>(),
+                                 n_starts, head->n_redo, depth_limit,
+                                 ctx->scratch[0].as<int32_t>(), stride, blk, hit_cap));
+        WalkHead again;
+        MCG_TRY(d2h(ctx, &again, blk, sizeof again));
+        MCG_TRY(sync(ctx));
+        head->total = again.total;
+        if (again.n_failed == 0) return MCG_OK;
+    }
+}
+
+int walk_check(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts, const int64_t *hit_start,
+               const int32_t *hit_count, const int32_t *hits, int64_t hit_cap, const int64_t *total) {
     if (ctx->g_vertices == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no graph resident (mcg_graph_load)");
     if (n_starts < 0 || hit_cap < 0 || !total || (n_starts > 0 && (!starts || !hit_start || !hit_count)) ||
         (hit_cap > 0 && !hits))
         return mcg_fail(ctx, MCG_ERR_ARG, "bad arguments");
-    *total = 0;
-    if (n_starts == 0) return MCG_OK;
     if (n_starts > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many start nodes");
+    return MCG_OK;
+}
+
+// starts up, walks (and the redo passes) done; ranges and hits stay in ctx->g_block
+int walk_run(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts, int depth_limit,
+             int64_t hit_cap, WalkHead *head, bool read_head) {
     MCG_TRY(check_ids(ctx, starts, n_starts, ctx->g_vertices, "starts"));
-    const int64_t n8 = (n_starts + 1) / 2 * 2;
-    const size_t head_bytes = 16 + 8 * static_cast<size_t>(n_starts) + 8 * static_cast<size_t>(n8);
-    MCG_TRY(mcg_reserve(ctx, ctx->g_block, head_bytes + 12 * static_cast<size_t>(hit_cap)));
+    MCG_TRY(mcg_reserve(ctx, ctx->g_block, walk_head_bytes(n_starts) + 12 * static_cast<size_t>(hit_cap)));
     MCG_TRY(mcg_reserve(ctx, ctx->g_starts, sizeof(int64_t) * n_starts));
     MCG_TRY(mcg_reserve(ctx, ctx->g_work, mcg_walk_work_bytes(n_starts)));
-    char *blk = ctx->g_block.as<char>();
     MCG_TRY(h2d(ctx, ctx->g_starts.p, starts, sizeof(int64_t) * n_starts));
     {
         TimerScope t(ctx, T_OTHER);
         MCG_TRY(mcg_k_walks(ctx, ctx->g_indptr.as<int64_t>(), ctx->g_indices.as<int32_t>(),
                             ctx->g_labels.as<int32_t>(), ctx->g_starts.as<int64_t>(), n_starts,
-                            depth_limit, ctx->g_work.as<int32_t>(), blk, hit_cap));
+                            depth_limit, ctx->g_work.as<int32_t>(), ctx->g_block.as<char>(), hit_cap));
     }
+    if (!read_head) return MCG_OK;
+    MCG_TRY(d2h(ctx, head, ctx->g_block.p, sizeof *head));
+    MCG_TRY(sync(ctx));
+    if (head->n_redo > 0) MCG_TRY(walk_redo(ctx, n_starts, depth_limit, hit_cap, head));
+    return MCG_OK;
+}
+
+int walk_fetch(mcg_ctx *ctx, int64_t n_starts, int64_t *hit_start, int32_t *hit_count,
+               int32_t *hits, int64_t total) {
+    TimerScope t(ctx, T_D2H);
+    const char *blk = ctx->g_block.as<char>();
+    MCG_TRY(d2h(ctx, hit_start, blk + 16, sizeof(int64_t) * n_starts));
+    MCG_TRY(d2h(ctx, hit_count, blk + 16 + 8 * n_starts, sizeof(int32_t) * n_starts));
+    MCG_TRY(d2h(ctx, hits, blk + walk_head_bytes(n_starts), 12 * static_cast<size_t>(total)));
+    return sync(ctx);
+}
+}  // namespace
+
+// The two halves of mcg_bfs_resident for the device pool: every device walks its share of the
+// start nodes, the totals give every share its place in the caller's hit list, and every device
+// copies straight there (no staging vectors on the host, no second memcpy).
+int mcg_bfs_run(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts, int depth_limit,
+                int64_t hit_cap, int64_t *total) {
+    MCG_ENTER(ctx);
+    *total = 0;
+    if (n_starts == 0) return MCG_OK;
+    if (ctx->g_vertices == 0) return mcg_fail(ctx, MCG_ERR_STATE, "no graph resident (mcg_graph_load)");
+    if (n_starts > 0x7fffffffLL) return mcg_fail(ctx, MCG_ERR_ARG, "too many start nodes");
+    WalkHead head;
+    MCG_TRY(walk_run(ctx, starts, n_starts, depth_limit, hit_cap, &head, true));
+    *total = head.total;
+    return MCG_OK;
+}
+
+int mcg_bfs_fetch(mcg_ctx *ctx, int64_t n_starts, int64_t *hit_start, int32_t *hit_count,
+                  int32_t *hits, int64_t total) {
+    MCG_ENTER(ctx);
+    if (n_starts == 0) return MCG_OK;
+    return walk_fetch(ctx, n_starts, hit_start, hit_count, hits, total);
+}
+
+extern "C" int mcg_bfs_resident(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts,
+                                int depth_limit, int64_t *hit_start, int32_t *hit_count,
+                                int32_t *hits, int64_t hit_cap, int64_t *total) {
+    MCG_ENTER(ctx);
+    MCG_TRY(walk_check(ctx, starts, n_starts, hit_start, hit_count, hits, hit_cap, total));
+    *total = 0;
+    if (n_starts == 0) return MCG_OK;
+    WalkHead head;
     // Small calls (the few contigs around one accepted contig) come back in ONE copy and one
     // synchronisation: header, ranges and the first hits speculatively, through pinned memory.
-    struct Head { long long total; int n_redo, n_failed; } head;
     const bool small = n_starts <= 4096;
-    const int64_t spec_hits = small ? std::min<int64_t>(hit_cap, 4 * n_starts + 256) : 0;
-    const size_t spec_bytes = head_bytes + 12 * static_cast<size_t>(spec_hits);
-    if (small) {
-        if (spec_bytes > ctx->g_pinned_cap) {
-            if (ctx->g_pinned) cudaFreeHost(ctx->g_pinned);
-            ctx->g_pinned = nullptr;
-            ctx->g_pinned_cap = 0;
-            const size_t want = std::max<size_t>(spec_bytes, 1 << 16);
-            if (cudaMallocHost(&ctx->g_pinned, want) != cudaSuccess)
-                return mcg_fail(ctx, MCG_ERR_NOMEM, "cudaMallocHost(%zu) failed", want);
-            ctx->g_pinned_cap = want;
-        }
-        MCG_TRY(d2h(ctx, ctx->g_pinned, blk, spec_bytes));
-        MCG_TRY(sync(ctx));
-        memcpy(&head, ctx->g_pinned, sizeof head);
-    } else {
-        MCG_TRY(d2h(ctx, &head, blk, sizeof head));
-        MCG_TRY(sync(ctx));
+    if (!small) {
+        MCG_TRY(walk_run(ctx, starts, n_starts, depth_limit, hit_cap, &head, true));
+        *total = head.total;
+        if (head.total > hit_cap) return MCG_OK;   // the caller comes back with a larger buffer
+        return walk_fetch(ctx, n_starts, hit_start, hit_count, hits, head.total);
     }
+    MCG_TRY(walk_run(ctx, starts, n_starts, depth_limit, hit_cap, &head, false));
+    const size_t head_bytes = walk_head_bytes(n_starts);
+    const int64_t spec_hits = std::min<int64_t>(hit_cap, 4 * n_starts + 256);
+    const size_t spec_bytes = head_bytes + 12 * static_cast<size_t>(spec_hits);
+    if (spec_bytes > ctx->g_pinned_cap) {
+        if (ctx->g_pinned) cudaFreeHost(ctx->g_pinned);
+        ctx->g_pinned = nullptr;
+        ctx->g_pinned_cap = 0;
+        const size_t want = std::max<size_t>(spec_bytes, 1 << 16);
+        if (cudaMallocHost(&ctx->g_pinned, want) != cudaSuccess)
+            return mcg_fail(ctx, MCG_ERR_NOMEM, "cudaMallocHost(%zu) failed", want);
+        ctx->g_pinned_cap = want;
+    }
+    MCG_TRY(d2h(ctx, ctx->g_pinned, ctx->g_block.p, spec_bytes));
+    MCG_TRY(sync(ctx));
+    memcpy(&head, ctx->g_pinned, sizeof head);
     bool redone = false;
     if (head.n_redo > 0) {
         redone = true;
-        for (int64_t stride = 4096;; stride *= 4) {
-            const size_t bytes = sizeof(int32_t) * static_cast<size_t>(stride) * head.n_redo;
-            if (bytes > (size_t(8) << 30))
-                return mcg_fail(ctx, MCG_ERR_NOMEM, "BFS work buffer would exceed 8 GiB");
-            MCG_TRY(mcg_reserve(ctx, ctx->scratch[0], bytes));
-            MCG_TRY(mcg_k_walks_redo(ctx, ctx->g_indptr.as<int64_t>(), ctx->g_indices.as<int32_t>(),
-                                     ctx->g_labels.as<int32_t>(), ctx->g_starts.as<int64_t>(),
-                                     n_starts, head.n_redo, depth_limit,
-                                     ctx->scratch[0].as<int32_t>(), stride, blk, hit_cap));
-            Head again;
-            MCG_TRY(d2h(ctx, &again, blk, sizeof again));
-            MCG_TRY(sync(ctx));
-            head.total = again.total;
-            if (again.n_failed == 0) break;
-        }
+        MCG_TRY(walk_redo(ctx, n_starts, depth_limit, hit_cap, &head));
     }
     *total = head.total;
     if (head.total > hit_cap) return MCG_OK;   // the caller comes back with a larger buffer
-    if (small && !redone && head.total <= spec_hits) {
+    if (!redone && head.total <= spec_hits) {
         const char *src = static_cast<const char *>(ctx->g_pinned);
         memcpy(hit_start, src + 16, sizeof(int64_t) * n_starts);
         memcpy(hit_count, src + 16 + 8 * n_starts, sizeof(int32_t) * n_starts);
         if (head.total) memcpy(hits, src + head_bytes, 12 * static_cast<size_t>(head.total));
         return MCG_OK;
     }
-    TimerScope t(ctx, T_D2H);
-    MCG_TRY(d2h(ctx, hit_start, blk + 16, sizeof(int64_t) * n_starts));
-    MCG_TRY(d2h(ctx, hit_count, blk + 16 + 8 * n_starts, sizeof(int32_t) * n_starts));
-    MCG_TRY(d2h(ctx, hits, blk + head_bytes, 12 * static_cast<size_t>(head.total)));
-    return sync(ctx);
+    return walk_fetch(ctx, n_starts, hit_start, hit_count, hits, head.total);
 }
 
 // Rules A / B for listed (query, bin) items: label_prop_utils.py:54-86 scores a candidate only

@@ -221,6 +221,11 @@ int mcg_k_fp64_peak(mcg_ctx *ctx, double *tflops);
 int mcg_k_prune_stats(mcg_ctx *ctx, int64_t stats[4]);
 
 // mcg_tc.cu
+// halves of mcg_bfs_resident for the device pool (mcg_api.cu)
+int mcg_bfs_run(mcg_ctx *ctx, const int64_t *starts, int64_t n_starts, int depth_limit,
+                int64_t hit_cap, int64_t *total);
+int mcg_bfs_fetch(mcg_ctx *ctx, int64_t n_starts, int64_t *hit_start, int32_t *hit_count,
+                  int32_t *hits, int64_t total);
 long long mcg_tc_ldf(long long bins);
 int mcg_k_tc_prep_bins(mcg_ctx *ctx, const ScoreSide &b);
 int mcg_k_tc_dist(mcg_ctx *ctx, const ScoreSide &a, long long bins, float *d_d2a, long long ldf,

@@ -426,34 +426,34 @@ extern "C" int mcg_pool_bfs(mcg_pool *pool, const int64_t *starts, int64_t n_sta
         });
     std::vector<int64_t> cut;
     split_even(n_starts, nd, &cut);
-    // every device fills a private list sized like the caller's share; the lists are then laid
-    // end to end in start order
-    std::vector<std::vector<int32_t>> part(nd);
+    // every device walks its share and keeps the hits; the totals lay the shares end to end in
+    // start order, and every device copies its list straight to its place in the caller's
     std::vector<int64_t> part_total(nd, 0);
     const int64_t share = hit_cap / nd + 1;
     int rc = pool_run(pool, [&](int i) -> int {
         const int64_t a = cut[i], b = cut[i + 1];
         if (b == a) return MCG_OK;
-        part[i].resize(static_cast<size_t>(3 * share));
+        int64_t cap = share;
         for (;;) {
-            const int64_t cap = static_cast<int64_t>(part[i].size() / 3);
-            MCG_TRY(mcg_bfs_resident(pool->ctx[i], starts + a, b - a, depth_limit, hit_start + a,
-                                     hit_count + a, part[i].data(), cap, &part_total[i]));
+            MCG_TRY(mcg_bfs_run(pool->ctx[i], starts + a, b - a, depth_limit, cap, &part_total[i]));
             if (part_total[i] <= cap) return MCG_OK;
-            part[i].resize(static_cast<size_t>(3 * part_total[i]));
+            cap = part_total[i];
         }
     });
     if (rc != MCG_OK) return rc;
-    int64_t sum = 0;
-    for (int i = 0; i < nd; ++i) sum += part_total[i];
-    *total = sum;
-    if (sum > hit_cap) return MCG_OK;
-    int64_t base = 0;
-    for (int i = 0; i < nd; ++i) {
-        if (part_total[i]) memcpy(hits + 3 * base, part[i].data(), 12 * static_cast<size_t>(part_total[i]));
-        if (base)
-            for (int64_t k = cut[i]; k < cut[i + 1]; ++k) hit_start[k] += base;
-        base += part_total[i];
-    }
+    std::vector<int64_t> base(nd + 1, 0);
+    for (int i = 0; i < nd; ++i) base[i + 1] = base[i] + part_total[i];
+    *total = base[nd];
+    if (base[nd] > hit_cap) return MCG_OK;
+    rc = pool_run(pool, [&](int i) -> int {
+        const int64_t a = cut[i], b = cut[i + 1];
+        if (b == a) return MCG_OK;
+        MCG_TRY(mcg_bfs_fetch(pool->ctx[i], b - a, hit_start + a, hit_count + a, hits + 3 * base[i],
+                              part_total[i]));
+        if (base[i])
+            for (int64_t k = a; k < b; ++k) hit_start[k] += base[i];
+        return MCG_OK;
+    });
+    if (rc != MCG_OK) return rc;
     return MCG_OK;
 }
