@@ -1238,7 +1238,8 @@ def main():
                      traffic=cap.get("scan_kernel"),
                      algorithmic_bytes=scan_bytes,
                      gbases_per_s=n_bases / (kernel_ms["scan"] * 1e-3) / 1e9,
-                     traffic_source=captured.get("source"),
+                     traffic_source=("%s (kernel source unchanged since commit %s)" % (
+                         cap.get("source"), cap.get("commit")) if cap.get("source") else None),
                      note="bound by the L1TEX load/store data pipe, not HBM (DESIGN.md 4.1): two "
                           "shared-memory wavefronts per 32 windows is the floor of a "
                           "byte-counter histogram")

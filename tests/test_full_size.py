@@ -3,6 +3,7 @@ oracle checks on seeded subsets (the oracle finishes those in seconds):
 
   config 2   100 000 contigs of 1-50 kb (1.25 Gbp), 10 samples, 200 bins
   config 3   one 8-GPU shard of the 1 M-contig set: 125 000 contigs, 50 samples, 500 bins
+  config 5   one 8-GPU shard of the 5 M-contig set: 625 000 contigs, 100 samples, 1000 bins
   config 4   Flye-style contigs of 10 kb-5 Mb (scaled to ~1.6 Gbp)
 
 Properties: every count row sums to len - 3; a contig's profile and its assignment do not
@@ -133,6 +134,19 @@ def test_config3_shard_full_size():
         tabs, blob = build(ctx, "megahit", 125000, 50, 500, 1003)
         check_scoring(ctx, tabs, blob, 150, 2)
         assert 0 <= ctx.last_redo_count() <= 125000
+    finally:
+        ctx.close()
+
+
+def test_config5_shard_full_size():
+    """One 8-GPU shard of configs[4]: 625 000 contigs x 1000 bins x 100 samples (the guarded
+    S > 30 path, 16 bin tiles, chunked rows), pruned == all pairs bit for bit, 120 seeded contigs
+    through the oracle."""
+    ctx = _lib.Context(0)
+    try:
+        tabs, blob = build(ctx, "megahit", 625000, 100, 1000, 1005)
+        check_scoring(ctx, tabs, blob, 120, 5)
+        assert 0 <= ctx.last_redo_count() <= 625000
     finally:
         ctx.close()
 
