@@ -38,8 +38,8 @@ if [ "${SKIP_NCU:-0}" != 1 ]; then
     echo "ncu cfg3 launch list exit: $?"
     # full captures: one launch of every kernel of the resident step
     MCG_BENCH_CONFIGS="" MCG_BENCH_NO_PYTHON_REF=1 timeout 1200 ncu --set full --clock-control none \
-        --import-source on -k regex:'scan_kernel|row_norms|cov_terms|tc_|bound_kernel|cand_|dist2|exact_d2|prob_kernel' \
-        --launch-skip 40 -c 24 -o $OUT/${TAG}_full -f \
+        --import-source on -k regex:'scan_kernel|row_norms|cov_terms|tc_|bound_|cand_|dist2|prob_kernel' \
+        --launch-skip 45 -c 28 -o $OUT/${TAG}_full -f \
         python bench.py --steps 2 --warmup 3 --e2e-steps 1 --cpu-budget 1 > $OUT/${TAG}_ncu_full.log 2>&1
     echo "ncu full exit: $?"
     python tools/ncu_summary.py $OUT/${TAG}_full.ncu-rep > $OUT/${TAG}_ncu_full_summary.txt 2>&1
