@@ -1200,15 +1200,19 @@ constexpr int kMaxSlabs = 64;      // 32-bin slabs per contig the candidate path
 
 // (c, log c) of the first kHeadSamples samples of every bin, sample-major, so that the 32 lanes
 // of bound_kernel (32 consecutive bins) read them coalesced: head[(2 q + {0,1}) * ldh + bin].
+// headf: the same pairs as float2 [q * ldh + bin] for the second-probe SEARCH of bound_kernel,
+// which only chooses a bin (any choice is valid) and waits for this table.
 __global__ void bin_head_kernel(ScoreSide B, int S, int nq, long long ldh,
-                                double *__restrict__ head) {
+                                double *__restrict__ head, float2 *__restrict__ headf) {
     const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (i >= B.n * nq) return;
     const long long j = i / nq;
     const int q = static_cast<int>(i - j * nq);
     const long long brow = B.index ? B.index[B.first + j] : (B.first + j);
-    head[(2 * q) * ldh + j] = B.cov[brow * S + q];
-    head[(2 * q + 1) * ldh + j] = B.logc[brow * S + q];
+    const double c = B.cov[brow * S + q], l = B.logc[brow * S + q];
+    head[(2 * q) * ldh + j] = c;
+    head[(2 * q + 1) * ldh + j] = l;
+    headf[q * ldh + j] = make_float2(static_cast<float>(c), static_cast<float>(l));
 }
 
 __device__ __forceinline__ void ld_v4(double (&v)[4], const double *p) {
@@ -1333,10 +1337,12 @@ __global__ void __launch_bounds__(256)
 bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long long ldc,
              const float *__restrict__ mrow, const double *__restrict__ head, long long ldh,
              const unsigned long long *__restrict__ tilemin, CandList cl,
-             int32_t *__restrict__ status, const BoundPre *__restrict__ pre) {
+             int32_t *__restrict__ status, const BoundPre *__restrict__ pre,
+             const float2 *__restrict__ headf) {
     __shared__ double ET[16];
     __shared__ double LT[128];
     __shared__ double HA[8][2 * kHeadSamples];   // per warp: (c, m) of the contig's first samples
+    __shared__ float HAF[8][2 * kHeadSamples];   // the same in float, for the second-probe search
     __shared__ unsigned MASK[8][kMaxSlabs];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < 16) ET[tid] = g_exp_table[tid];
@@ -1364,8 +1370,12 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
             const BoundPre bp = pre[r];
             w_pre = bp.w; thr_pre = bp.thr2; u_tail = bp.u_tail; cov_upper = bp.cov_upper; jm = bp.jm;
             if (lane < nq) {
-                HA[wid][2 * lane] = A.cov[arow * S + lane];
-                HA[wid][2 * lane + 1] = -(A.lgam[arow * S + lane] + c_math.log_floor);
+                const double hc = A.cov[arow * S + lane];
+                const double hm = -(A.lgam[arow * S + lane] + c_math.log_floor);
+                HA[wid][2 * lane] = hc;
+                HA[wid][2 * lane + 1] = hm;
+                HAF[wid][2 * lane] = static_cast<float>(hc);
+                HAF[wid][2 * lane + 1] = static_cast<float>(hm);
             }
             __syncwarp();
         } else {
@@ -1402,7 +1412,10 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
             e = e > 0.0 ? e : 0.0;
             u += e;
             if (q >= nq) u_tail += e;
-            if (q < nq) { HA[wid][2 * q] = ac; HA[wid][2 * q + 1] = am; }
+            if (q < nq) {
+                HA[wid][2 * q] = ac; HA[wid][2 * q + 1] = am;
+                HAF[wid][2 * q] = static_cast<float>(ac); HAF[wid][2 * q + 1] = static_cast<float>(am);
+            }
         }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
@@ -1450,15 +1463,18 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
                 const int j = 32 * sb + lane;
                 if (j < B.n) {
                     const double dd = fmax(static_cast<double>(row[j]) - mg, 0.0);
-                    double e1 = 0.0;
-                    const double *hp = head + j;
-                    // (four samples' loads in flight: this loop waits for L2, ncu r02o)
+                    // float terms from the float2 table: this pass only CHOOSES the bin to probe
+                    // (any choice is valid) and it waits for the table (ncu r02o: 39 % of the
+                    // kernel's samples at S = 50): half the bytes, one load per sample
+                    float e1 = 0.f;
+                    const float2 *hf = headf + j;
 #pragma unroll 4
                     for (int q = 0; q < nq; ++q) {
-                        const double bc = hp[(2 * q) * ldh], bl = hp[(2 * q + 1) * ldh];
-                        add_poisson_excess(e1, HA[wid][2 * q], HA[wid][2 * q + 1], bc, bl);
+                        const float2 b = __ldg(hf + q * ldh);
+                        const float d = fmaf(HAF[wid][2 * q], b.y, HAF[wid][2 * q + 1]) - b.x;
+                        e1 += d > 0.f ? d : 0.f;
                     }
-                    const double v = fma(c_math.prune_4a * 0.25, dd, -e1);
+                    const double v = fma(c_math.prune_4a * 0.25, dd, -static_cast<double>(e1));
                     if (v < lb) { lb = v; jb = j; }
                 }
             }
@@ -2073,6 +2089,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
     ctx->redo_valid = guard;
     CandList cl = {nullptr, 0, nullptr, nullptr, nullptr, nullptr};
     unsigned long long *tilemin = nullptr;   // per (row, 64-bin tile) smallest d^2, from dist2_kernel
+    float2 *headf = nullptr;
     ctx->cand_valid = false;
     if (use_cand) {
         // [total | pad] [start rows] [count rows] [pair cap] [w cap]
@@ -2091,11 +2108,12 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         ctx->cand_valid = true;
         ctx->cand_cap = cap;
         const int nq = S < kHeadSamples ? S : kHeadSamples;
-        // [head table 2 nq ldc doubles] [tile minima need_rows x b_tiles]
-        MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(double) * (2 * nq * ldc + need_rows * b_tiles)));
-        tilemin = reinterpret_cast<unsigned long long *>(ctx->scratch[1].as<double>() + 2 * nq * ldc);
+        // [head table 2 nq ldc doubles] [its float2 copy nq ldc] [tile minima need_rows x b_tiles]
+        MCG_TRY(mcg_reserve(ctx, ctx->scratch[1], sizeof(double) * (3 * nq * ldc + need_rows * b_tiles)));
+        headf = reinterpret_cast<float2 *>(ctx->scratch[1].as<double>() + 2 * nq * ldc);
+        tilemin = reinterpret_cast<unsigned long long *>(ctx->scratch[1].as<double>() + 3 * nq * ldc);
         bin_head_kernel<<<blocks_for(b.n * nq, 256), 256, 0, ctx->stream>>>(
-            b, S, nq, ldc, ctx->scratch[1].as<double>());
+            b, S, nq, ldc, ctx->scratch[1].as<double>(), headf);
         MCG_KERNEL_CHECK(ctx);
     }
     // distances for the bound: the tensor-core estimate (default) or dist2_kernel's exact matrix
@@ -2163,15 +2181,15 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
                 MCG_KERNEL_CHECK(ctx);
                 bound_kernel<float, true><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
                     ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
-                    d_status, pre);
+                    d_status, pre, headf);
             } else if (use_tc)
                 bound_kernel<float, false><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
                     ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
-                    d_status, nullptr);
+                    d_status, nullptr, headf);
             else
                 bound_kernel<double, false><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
                     ac, b, S, d2, ldc, nullptr, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
-                    d_status, nullptr);
+                    d_status, nullptr, headf);
             MCG_KERNEL_CHECK(ctx);
             const unsigned sb = static_cast<unsigned>(8 * ctx->sm_count);
             if (guard) {
