@@ -1668,21 +1668,53 @@ cand_score_kernel(ScoreSide A, ScoreSide B, int S, const double *__restrict__ d2
 }
 
 // First minimum of a contig's candidates and the bookkeeping of prob_kernel's last bin group.
+// One lane per contig walks a short list (the common case: 1-20 candidates); a contig that is
+// far from every centroid lists every bin (hundreds), and that one serial walk used to set the
+// kernel's time (77 us at config 3 against 6 us at config 2): lists beyond 32 entries are taken
+// by the whole warp, one after the other, lanes striding over the list.  (weight, position) is
+// compared lexicographically, which is the sequential loop's "first position of the smallest
+// weight".
 template <bool GUARD>
 __global__ void __launch_bounds__(256)
 cand_argmin_kernel(ScoreSide A, CandList cl, ScoreOut out, RedoList redo) {
     if (*cl.total > cl.cap) return;
+    const int lane = threadIdx.x & 31;
     const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (r >= A.n) return;
-    const int lo = cl.start[r], hi = lo + cl.count[r];
-    double bw = 0.0;
-    int bi = -1;
+    const bool live = r < A.n;
+    const int lo = live ? cl.start[r] : 0, cnt = live ? cl.count[r] : 0;
+    const int kNone = 0x7fffffff;
+    double bw = INFINITY;
+    int bp = kNone;              // position of the best candidate; none yet
     bool def = false;
-    for (int i = lo; i < hi; ++i) {
-        const double w = cl.w[i];
-        if (w != w) { def = true; continue; }
-        if (bi < 0 || w < bw) { bw = w; bi = cl.pair[i].y; }
+    const bool wide = cnt > 32;
+    if (!wide)
+        for (int i = lo; i < lo + cnt; ++i) {
+            const double w = cl.w[i];
+            if (w != w) { def = true; continue; }
+            if (bp == kNone || w < bw) { bw = w; bp = i; }
+        }
+    for (unsigned todo = __ballot_sync(0xffffffffu, wide); todo; todo &= todo - 1) {
+        const int src = __ffs(todo) - 1;
+        const int lo_s = __shfl_sync(0xffffffffu, lo, src), hi_s = lo_s + __shfl_sync(0xffffffffu, cnt, src);
+        double w1 = INFINITY;
+        int p1 = kNone;
+        bool d1 = false;
+        for (int i = lo_s + lane; i < hi_s; i += 32) {
+            const double w = cl.w[i];
+            if (w != w) { d1 = true; continue; }
+            if (p1 == kNone || w < w1) { w1 = w; p1 = i; }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ow = __shfl_xor_sync(0xffffffffu, w1, m);
+            const int op = __shfl_xor_sync(0xffffffffu, p1, m);
+            if (op != kNone && (p1 == kNone || ow < w1 || (ow == w1 && op < p1))) { w1 = ow; p1 = op; }
+        }
+        d1 = __any_sync(0xffffffffu, d1);
+        if (lane == src) { bw = w1; bp = p1; def = d1; }
     }
+    if (!live) return;
+    const int bi = bp == kNone ? -1 : cl.pair[bp].y;
     const bool none = (bi < 0) || (bw == MCG_MAX_WEIGHT);   // label_prop_utils.py:342-345
     if (out.argmin) out.argmin[A.first + r] = none ? -1 : bi;
     if (out.wmin) out.wmin[A.first + r] = none ? MCG_MAX_WEIGHT : bw;
