@@ -1224,7 +1224,8 @@ __device__ __forceinline__ void ld_v4(double (&v)[4], const double *p) {
 // nearest centroid, the distance threshold that follows from it, and the coverage ceilings.
 struct BoundPre {
     double w, thr2, u_tail, cov_upper;
-    int jm, pad;
+    int jm;
+    int done;   // the pre-pass listed this contig's candidates itself (see bound_pre_kernel)
 };
 
 __device__ __forceinline__ double prune_threshold(double wv, double cov_upper) {
@@ -1243,10 +1244,17 @@ __device__ __forceinline__ double prune_threshold(double wv, double cov_upper) {
 // contig that are the same in all 32 lanes (ncu source page, r02h); here it is ~20.  The sums
 // run in sample order instead of a shuffle tree: W is a bound used with a 1e-9 margin, not a
 // result.
+//
+// A contig whose every OTHER bin is already beyond that threshold by the distance alone -- the
+// minima of the other tiles and the second smallest d2a of the nearest tile, the same one-sided
+// comparisons bound_kernel makes -- has at most one candidate, its nearest centroid: the lane
+// runs bound_kernel's tests on that one bin and writes the list entry itself (`done`), and
+// bound_kernel skips the contig.  At config 2 that is ~85 % of the contigs.
 __global__ void __launch_bounds__(128)
 bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, long long ldc,
                  const float *__restrict__ mrow, const unsigned long long *__restrict__ tilemin,
-                 BoundPre *__restrict__ pre, int32_t *__restrict__ status) {
+                 BoundPre *__restrict__ pre, int32_t *__restrict__ status, CandList cl,
+                 int *__restrict__ todo) {   // todo[0] = count, todo[1 ..] = contigs left for bound_kernel
     __shared__ double ET[16];
     __shared__ double LT[128];
     const int tid = threadIdx.x;
@@ -1268,15 +1276,21 @@ bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, 
         if (key < bk) { bk = key; bt = t; }
     }
     const float *row = d2 + rr * ldc + 64 * bt;
-    float dmf = INFINITY;
+    float dmf = INFINITY, second = INFINITY;   // smallest and second smallest d2a of the tile
     int jm = 64 * bt;
+    bool odd = false;                          // a NaN in the tile: bound_kernel keeps such a bin
+    auto look = [&](float v, int j) {
+        if (v < dmf) { second = dmf; dmf = v; jm = j; }
+        else if (v < second) second = v;
+        if (v != v) odd = true;
+    };
 #pragma unroll 4
     for (int i = 0; i < 64; i += 4) {
         const float4 v = *reinterpret_cast<const float4 *>(row + i);   // padding reads +inf
-        if (v.x < dmf) { dmf = v.x; jm = 64 * bt + i; }
-        if (v.y < dmf) { dmf = v.y; jm = 64 * bt + i + 1; }
-        if (v.z < dmf) { dmf = v.z; jm = 64 * bt + i + 2; }
-        if (v.w < dmf) { dmf = v.w; jm = 64 * bt + i + 3; }
+        look(v.x, 64 * bt + i);
+        look(v.y, 64 * bt + i + 1);
+        look(v.z, 64 * bt + i + 2);
+        look(v.w, 64 * bt + i + 3);
     }
     if (jm >= nb) { jm = 0; dmf = INFINITY; }
     const double mg = static_cast<double>(mrow[rr]);
@@ -1286,13 +1300,14 @@ bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, 
     const long long brow = B.index ? B.index[B.first + jm] : (B.first + jm);
     const double *ac_p = A.cov + arow * S, *al_p = A.logc + arow * S, *ag_p = A.lgam + arow * S;
     const double *bc_p = B.cov + brow * S, *bl_p = B.logc + brow * S, *bg_p = B.lgam + brow * S;
-    double u = 0.0, u_tail = 0.0, s1 = 0.0, s2 = 0.0;
+    double u = 0.0, u_tail = 0.0, s1 = 0.0, s2 = 0.0, e_head = 0.0;
     auto sample = [&](int q, double ac, double al, double ag, double bc, double bl, double bg) {
         const double am = -(ag + c_math.log_floor);
         double e = fma(ac, al, am) - ac;   // the most this sample can add
         e = e > 0.0 ? e : 0.0;
         u += e;
         if (q >= nq) u_tail += e;
+        if (q == nq) e_head = s1;          // the head excess of bound_kernel's second test
         add_poisson_excess(s1, ac, am, bc, bl);
         add_poisson_excess(s2, bc, -(bg + c_math.log_floor), ac, al);
     };
@@ -1313,6 +1328,7 @@ bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, 
     if (cov_upper > 0.0) cov_upper = 0.0;
     const double lpc = log_comp_prob_warp(ok ? dd : 0.01, ET, LT, status);
     const double w = ok ? -(lpc + sl + (s1 < s2 ? s1 : s2)) * c_math.inv_ln10 : INFINITY;
+    if (S <= nq) e_head = s1;
     if (live) {
         BoundPre out;
         out.w = w;
@@ -1320,8 +1336,36 @@ bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, 
         out.u_tail = u_tail;
         out.cov_upper = cov_upper;
         out.jm = jm;
-        out.pad = 0;
+        // every other bin beyond the threshold by the distance alone (lower ends)?
+        bool alone = out.thr2 < INFINITY && !odd &&
+                     fmax(static_cast<double>(second) - mg, 0.0) > out.thr2;
+        for (int t = 0; t < nbt && alone; ++t) {
+            if (t == bt) continue;
+            const unsigned long long key = tilemin[rr * nbt + t];
+            const double lb = __longlong_as_double(static_cast<long long>(
+                key <= 0x7ff0000000000000ull ? key : 0x7ff0000000000000ull));
+            if (!(lb > out.thr2)) alone = false;
+        }
+        out.done = alone ? 1 : 0;
         pre[r] = out;
+        if (!alone) todo[1 + atomicAdd(todo, 1)] = static_cast<int>(r);
+        if (alone) {
+            // bound_kernel's tests for the one bin left
+            const double raw = static_cast<double>(dmf);
+            const double dlo = fmax(raw - mg, 0.0);
+            bool keep = !(dlo > out.thr2);
+            if (dlo > 0.0405 && raw + mg < 1.5) keep = false;
+            const double slack = w * (1.0 + 1e-9) * c_gauss.ln10 + sl + u_tail * (1.0 + 1e-9) -
+                                 c_math.prune_c;
+            if (fma(c_math.prune_4a * 0.25, dlo, -e_head * (1.0 + 1e-9)) > slack) keep = false;
+            int at = 0;
+            if (keep) {
+                at = atomicAdd(cl.total, 1);
+                if (at < cl.cap) cl.pair[at] = make_int2(static_cast<int>(r), jm);
+            }
+            cl.start[r] = at;
+            cl.count[r] = keep ? 1 : 0;
+        }
     }
 }
 
@@ -1338,7 +1382,7 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
              const float *__restrict__ mrow, const double *__restrict__ head, long long ldh,
              const unsigned long long *__restrict__ tilemin, CandList cl,
              int32_t *__restrict__ status, const BoundPre *__restrict__ pre,
-             const float2 *__restrict__ headf) {
+             const float2 *__restrict__ headf, const int *__restrict__ todo) {
     __shared__ double ET[16];
     __shared__ double LT[128];
     __shared__ double HA[8][2 * kHeadSamples];   // per warp: (c, m) of the contig's first samples
@@ -1351,8 +1395,11 @@ bound_kernel(ScoreSide A, ScoreSide B, int S, const D2T *__restrict__ d2, long l
     const int nq = S < kHeadSamples ? S : kHeadSamples;
     const double sl = static_cast<double>(S) * c_math.log_floor;
     const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-    for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wid; r < A.n;
-         r += n_warps) {
+    // PRE: the contigs the pre-pass left (it listed the single candidate of the others itself)
+    const long long n_work = PRE ? todo[0] : A.n;
+    for (long long it = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wid; it < n_work;
+         it += n_warps) {
+        const long long r = PRE ? todo[1 + it] : it;
         const D2T *row = d2 + r * ldc;
         const double mg = mrow ? static_cast<double>(mrow[r]) : 0.0;
         // dist2_kernel left the smallest d^2 of the row in every 64-bin tile (ordered bits):
@@ -2153,6 +2200,7 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
     const long long ldf = mcg_tc_ldf(b.n);
     float *d2a = nullptr, *mrow = nullptr;
     BoundPre *pre = nullptr;
+    int *todo = nullptr;
     // the lane-per-contig pre-pass pays where the per-contig scalar work dominates bound_kernel
     // (S <= 30; measured: cfg2 probability phase 0.280 -> 0.248 ms, cfg3 / cfg5 shards +2 %)
     const bool bound_single = guard || getenv("MCG_BOUND_SINGLE") != nullptr;
@@ -2161,10 +2209,12 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         MCG_TRY(mcg_reserve(ctx, ctx->tc_d2a, sizeof(float) * rows_pad * ldf));
         // [margin need_rows floats, padded to 16 bytes] [BoundPre need_rows]
         const size_t mrow_bytes = (sizeof(float) * need_rows + 15) / 16 * 16;
-        MCG_TRY(mcg_reserve(ctx, ctx->tc_mrow, mrow_bytes + sizeof(BoundPre) * need_rows));
+        MCG_TRY(mcg_reserve(ctx, ctx->tc_mrow,
+                            mrow_bytes + sizeof(BoundPre) * need_rows + sizeof(int) * (need_rows + 4)));
         d2a = ctx->tc_d2a.as<float>();
         mrow = ctx->tc_mrow.as<float>();
         pre = reinterpret_cast<BoundPre *>(ctx->tc_mrow.as<char>() + mrow_bytes);
+        todo = reinterpret_cast<int *>(pre + need_rows);
         MCG_TRY(mcg_k_tc_prep_bins(ctx, b));
     }
     const CandGate gate = {cl.total, cl.cap};
@@ -2208,20 +2258,21 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
             long long bb = (ac.n + 7) / 8;
             if (bb > 8LL * ctx->sm_count) bb = 8LL * ctx->sm_count;
             if (use_tc && !bound_single) {
+                MCG_CUDA(ctx, cudaMemsetAsync(todo, 0, sizeof(int), ctx->stream));
                 bound_pre_kernel<<<blocks_for(ac.n, 128), 128, 0, ctx->stream>>>(
-                    ac, b, S, d2a, ldf, mrow, tilemin, pre, d_status);
+                    ac, b, S, d2a, ldf, mrow, tilemin, pre, d_status, cl, todo);
                 MCG_KERNEL_CHECK(ctx);
                 bound_kernel<float, true><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
                     ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
-                    d_status, pre, headf);
+                    d_status, pre, headf, todo);
             } else if (use_tc)
                 bound_kernel<float, false><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
                     ac, b, S, d2a, ldf, mrow, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
-                    d_status, nullptr, headf);
+                    d_status, nullptr, headf, nullptr);
             else
                 bound_kernel<double, false><<<static_cast<unsigned>(bb), 256, 0, ctx->stream>>>(
                     ac, b, S, d2, ldc, nullptr, ctx->scratch[1].as<double>(), ldc, tilemin, cl,
-                    d_status, nullptr, headf);
+                    d_status, nullptr, headf, nullptr);
             MCG_KERNEL_CHECK(ctx);
             const unsigned sb = static_cast<unsigned>(8 * ctx->sm_count);
             if (guard) {
