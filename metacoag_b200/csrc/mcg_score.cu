@@ -2201,9 +2201,10 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
     float *d2a = nullptr, *mrow = nullptr;
     BoundPre *pre = nullptr;
     int *todo = nullptr;
-    // the lane-per-contig pre-pass pays where the per-contig scalar work dominates bound_kernel
-    // (S <= 30; measured: cfg2 probability phase 0.280 -> 0.248 ms, cfg3 / cfg5 shards +2 %)
-    const bool bound_single = guard || getenv("MCG_BOUND_SINGLE") != nullptr;
+    // MCG_BOUND_SINGLE: bound_kernel without the lane-per-contig pre-pass (A/B switch; measured
+    // with it: config 2 probability phase 0.280 -> 0.151 ms, config-3 shard 0.98 -> 0.84 ms,
+    // config-5 chunk 1.05 -> 1.00 ms)
+    const bool bound_single = getenv("MCG_BOUND_SINGLE") != nullptr;
     if (use_tc) {
         const long long rows_pad = (need_rows + 127) / 128 * 128;
         MCG_TRY(mcg_reserve(ctx, ctx->tc_d2a, sizeof(float) * rows_pad * ldf));
