@@ -1320,6 +1320,19 @@ bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, 
 #pragma unroll
             for (int k = 0; k < 4; ++k) sample(h + k, ac[k], al[k], ag[k], bc[k], bl[k], bg[k]);
         }
+    } else if ((S & 1) == 0) {
+        // rows of an even S are 16-byte aligned: two samples per load
+#pragma unroll 2
+        for (int h = 0; h < S; h += 2) {
+            const double2 ac = *reinterpret_cast<const double2 *>(ac_p + h);
+            const double2 al = *reinterpret_cast<const double2 *>(al_p + h);
+            const double2 ag = *reinterpret_cast<const double2 *>(ag_p + h);
+            const double2 bc = *reinterpret_cast<const double2 *>(bc_p + h);
+            const double2 bl = *reinterpret_cast<const double2 *>(bl_p + h);
+            const double2 bg = *reinterpret_cast<const double2 *>(bg_p + h);
+            sample(h, ac.x, al.x, ag.x, bc.x, bl.x, bg.x);
+            sample(h + 1, ac.y, al.y, ag.y, bc.y, bl.y, bg.y);
+        }
     } else {
 #pragma unroll 2
         for (int q = 0; q < S; ++q) sample(q, ac_p[q], al_p[q], ag_p[q], bc_p[q], bl_p[q], bg_p[q]);
