@@ -19,11 +19,15 @@
 // prob_product > 0 branch through underflow), with log(c) and lgamma(c+1) hoisted per
 // (row, sample) by cov_terms_kernel.
 //
-// Rule C on large batches (every long contig against every bin): dist2_kernel (the d^2 matrix on
-// the FP64 tensor path, plus the smallest d^2 per row and 64-bin tile), then either prob_kernel
-// over every pair or, by default, the branch and bound: bound_kernel lists the bins that can
-// still beat the weight of the contig's nearest centroid, cand_score_kernel scores exactly
-// those, cand_argmin_kernel takes the first minimum (same bits as the all-pairs pass).
+// Rule C on large batches (every long contig against every bin), by default a branch and bound:
+// the all-pairs distances as a tensor-core BOUND with a stated margin (mcg_tc.cu: d2a, plus the
+// smallest lower bound per row and 64-bin tile); bound_pre_kernel (one lane per contig: nearest
+// centroid, its weight W, the distance threshold that follows; it lists the single candidate of
+// the contigs whose other bins are all beyond that threshold); bound_kernel (one warp per
+// remaining contig: second probe, candidate list); cand_score_kernel (float64 d^2 and weight of
+// exactly the listed pairs); cand_argmin_kernel (first minimum).  Same bits as the all-pairs
+// pass, which is dist2_kernel (the float64 d^2 matrix on the FP64 tensor path) + prob_kernel:
+// taken when the weight matrix is wanted, with MCG_PRUNE=0, or when the list overflows.
 #include "mcg_internal.cuh"
 #include <cstdlib>
 
@@ -1249,7 +1253,7 @@ __device__ __forceinline__ double prune_threshold(double wv, double cov_upper) {
 // minima of the other tiles and the second smallest d2a of the nearest tile, the same one-sided
 // comparisons bound_kernel makes -- has at most one candidate, its nearest centroid: the lane
 // runs bound_kernel's tests on that one bin and writes the list entry itself (`done`), and
-// bound_kernel skips the contig.  At config 2 that is ~85 % of the contigs.
+// bound_kernel never sees the contig (it walks the compacted list `todo` of the others).
 __global__ void __launch_bounds__(128)
 bound_pre_kernel(ScoreSide A, ScoreSide B, int S, const float *__restrict__ d2, long long ldc,
                  const float *__restrict__ mrow, const unsigned long long *__restrict__ tilemin,
