@@ -2267,7 +2267,16 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
         }
         mcg_timer_end(ctx, T_DIST);
         long long blocks = (ac.n + warps * kProbRows - 1) / (warps * kProbRows);
-        const long long cap = 4LL * ctx->sm_count * 4;
+        long long cap = 4LL * ctx->sm_count * 4;
+        if (use_cand) {
+            // Behind the candidate path these launches leave at once unless the list overflowed
+            // (device-side gate), one launch per bin group: 31 groups x 10 chunks of 2048 CTAs
+            // with 200 KB of shared memory each were 1.8 ms = 10 % of a config-5 shard step
+            // (ncu launch list r02K).  One resident wave is enough: the kernel strides over its
+            // rows, so the real fallback runs the same work on fewer, longer CTAs.
+            const long long per_sm = prob_smem > 110 * 1024 ? 1 : (prob_smem > 56 * 1024 ? 2 : 4);
+            cap = per_sm * ctx->sm_count;
+        }
         if (blocks > cap) blocks = cap;
         mcg_timer_begin(ctx, T_PROB);
         if (use_cand) {
