@@ -2157,8 +2157,11 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
 
         if (ctx->device < 64) attr[ctx->device] = true;
     }
-    // rows per chunk: <= 512 MiB of scratch, whole tiles
-    long long rows_per_chunk = (512LL << 20) / (sizeof(double) * ldc);
+    // rows per chunk: <= 2 GiB of (fallback) float64 scratch, whole tiles.  Every chunk costs a
+    // fixed set of launches (at S = 100, B = 1000 that is 31 gated bin-group launches next to the
+    // working kernels), so chunks are as large as 180 GB of HBM comfortably allow: 262 144 rows
+    // at B = 1000 (d2a 1 GiB, operands 0.23 GiB, candidate list <= 1 GiB)
+    long long rows_per_chunk = (2048LL << 20) / (sizeof(double) * ldc);
     rows_per_chunk = (rows_per_chunk / kTile) * kTile;
     if (rows_per_chunk < kTile) rows_per_chunk = kTile;
     const long long need_rows = ((a.n < rows_per_chunk ? a.n : rows_per_chunk) + kTile - 1) /
