@@ -2157,11 +2157,13 @@ static int split_rule_c(mcg_ctx *ctx, const ScoreSide &a, const ScoreSide &b, in
 
         if (ctx->device < 64) attr[ctx->device] = true;
     }
-    // rows per chunk: <= 2 GiB of (fallback) float64 scratch, whole tiles.  Every chunk costs a
+    // rows per chunk: <= 4 GiB of (fallback) float64 scratch, whole tiles.  Every chunk costs a
     // fixed set of launches (at S = 100, B = 1000 that is 31 gated bin-group launches next to the
-    // working kernels), so chunks are as large as 180 GB of HBM comfortably allow: 262 144 rows
-    // at B = 1000 (d2a 1 GiB, operands 0.23 GiB, candidate list <= 1 GiB)
-    long long rows_per_chunk = (2048LL << 20) / (sizeof(double) * ldc);
+    // working kernels) and a tail per kernel, so chunks are as large as 180 GB of HBM
+    // comfortably allow: 524 288 rows at B = 1000 (d2a 2 GiB, operands 0.47 GiB, candidate list
+    // <= 2 GiB).  Measured, config 3 at size / config-5 shard: 512 MiB 13.05 / 17.2 ms, 2 GiB
+    // 10.19 / 15.0 ms, 4 GiB 10.00 / 14.6 ms.
+    long long rows_per_chunk = (4096LL << 20) / (sizeof(double) * ldc);
     rows_per_chunk = (rows_per_chunk / kTile) * kTile;
     if (rows_per_chunk < kTile) rows_per_chunk = kTile;
     const long long need_rows = ((a.n < rows_per_chunk ? a.n : rows_per_chunk) + kTile - 1) /
